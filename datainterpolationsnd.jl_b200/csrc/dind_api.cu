@@ -1,0 +1,747 @@
+// dind_api.cu — the C ABI of libdind.so (include/dind.h): handle lifecycle, validation with
+// the reference's assert semantics, device-resident layout of knots / t_eval / u, kernel
+// dispatch.  There is no CPU evaluation path in this library.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dind.h"
+#include "dind_kernels.h"
+
+using namespace dind;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            cudaGetLastError();                                                                       \
+            return fail(DIND_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                             \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (bytes == 0) bytes = 16;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct AxisTable {
+    int order = -1;
+    DevBuf i0, w, flag;
+};
+
+struct DimState {
+    bool set = false;
+    int kind = 0, degree = 0, left = 1;
+    std::vector<double> t;          // distinct knots (exact for both element types)
+    std::vector<int64_t> mult;
+    std::vector<double> knots;      // t, or knots_all for BSpline
+    int width = 0;
+    int64_t n_u = 0;                // expected size(u, dim)
+    DevBuf d_knots, d_keys, d_recip;
+    // t_eval
+    bool teval_set = false;
+    const void* d_teval = nullptr;  // device pointer (owned copy or borrowed)
+    DevBuf teval_owned;
+    int64_t n_eval = 0;
+    int max_deriv = 0;
+    DevBuf d_idx;
+    bool idx_valid = false;
+    AxisTable table;
+    void invalidate_caches() {
+        idx_valid = false;
+        table.order = -1;
+    }
+    void release() {
+        d_knots.release(); d_keys.release(); d_recip.release(); teval_owned.release();
+        d_idx.release(); table.i0.release(); table.w.release(); table.flag.release();
+    }
+};
+
+}  // namespace
+
+struct dind_interp_s {
+    int n_in = 0, dtype = 0, device = 0;
+    size_t esz = 4;
+    cudaStream_t stream = nullptr;
+    DimState dims[MAXN];
+    // u
+    bool u_set = false;
+    const void* d_u = nullptr;
+    DevBuf u_owned;
+    std::vector<int64_t> u_dims;
+    int64_t comp_stride = 0, n_comp = 1;
+    // NURBS weights
+    bool w_set = false;
+    const void* d_w = nullptr;
+    DevBuf w_owned;
+    DevBuf uw;          // u pre-multiplied by the weights
+    bool uw_valid = false;
+    // staging
+    DevBuf out_stage;
+    DevBuf pts_stage[MAXN];
+    std::string last_kernel = "none";
+    int64_t launches = 0;
+};
+
+namespace {
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+template <typename T>
+int upload_dim(dind_interp_s* h, DimState& D) {
+    using K = typename KeyOf<T>::type;
+    const int n = (int)D.knots.size();
+    std::vector<T> kn(n);
+    std::vector<K> keys(n);
+    for (int i = 0; i < n; ++i) {
+        kn[i] = (T)D.knots[i];
+        keys[i] = to_key(kn[i]);
+    }
+    std::vector<T> recip;
+    if (D.kind == LINEAR) {
+        recip.resize(n > 1 ? n - 1 : 1);
+        for (int c = 0; c + 1 < n; ++c) recip[c] = T(1) / (kn[c + 1] - kn[c]);
+    } else if (D.kind == BSPLINE) {
+        const int p = D.degree;
+        recip.assign((size_t)(p > 0 ? p : 1) * n, T(0));
+        for (int d = 1; d <= p; ++d)
+            for (int i = 0; i + d < n; ++i) {
+                const T span = kn[i + d] - kn[i];
+                recip[(size_t)(d - 1) * n + i] = (span == T(0)) ? T(0) : T(1) / span;   // safe_div, spline_utils.jl:22
+            }
+    } else {
+        recip.assign(1, T(0));
+    }
+    CUDA_TRY(D.d_knots.ensure(n * sizeof(T)));
+    CUDA_TRY(D.d_keys.ensure(n * sizeof(K)));
+    CUDA_TRY(D.d_recip.ensure(recip.size() * sizeof(T)));
+    CUDA_TRY(cudaMemcpyAsync(D.d_knots.p, kn.data(), n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(D.d_keys.p, keys.data(), n * sizeof(K), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(D.d_recip.p, recip.data(), recip.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));   // host vectors go out of scope
+    return DIND_OK;
+}
+
+template <typename T>
+DimParams<T> make_dim_params(const dind_interp_s* h, const DimState& D, int dim, int order) {
+    using K = typename KeyOf<T>::type;
+    DimParams<T> P;
+    memset(&P, 0, sizeof P);
+    P.knots = (const T*)D.d_knots.p;
+    P.keys = (const K*)D.d_keys.p;
+    P.recip = (const T*)D.d_recip.p;
+    P.t_eval = (const T*)D.d_teval;
+    P.idx_eval = D.idx_valid ? (const int32_t*)D.d_idx.p : nullptr;
+    P.tab_i0 = (const int32_t*)D.table.i0.p;
+    P.tab_w = (const T*)D.table.w.p;
+    P.tab_flag = (const uint8_t*)D.table.flag.p;
+    P.n_eval = D.n_eval;
+    int64_t stride = 1;
+    for (int i = 0; i < dim; ++i) stride *= h->u_set ? h->u_dims[i] : 1;
+    P.u_stride = stride;
+    P.n_knots = (int32_t)D.knots.size();
+    P.kind = D.kind;
+    P.degree = D.degree;
+    P.width = D.width;
+    P.n_u = (int32_t)D.n_u;
+    P.order = order;
+    return P;
+}
+
+int check_handle(dind_handle_t h) {
+    if (!h) return fail(DIND_ERR_INVALID_ARGUMENT, "null handle");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return fail(DIND_ERR_CUDA, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e));
+    return DIND_OK;
+}
+
+int check_dim(dind_handle_t h, int dim) {
+    if (dim < 0 || dim >= h->n_in) return fail(DIND_ERR_INVALID_ARGUMENT, "dimension %d out of range 0..%d", dim, h->n_in - 1);
+    return DIND_OK;
+}
+
+template <typename T>
+int ensure_idx(dind_interp_s* h, int dim) {
+    DimState& D = h->dims[dim];
+    if (D.idx_valid) return DIND_OK;
+    CUDA_TRY(D.d_idx.ensure((size_t)D.n_eval * sizeof(int32_t)));
+    DimParams<T> P = make_dim_params<T>(h, D, dim, 0);
+    CUDA_TRY(launch_idx<T>(P, (int32_t*)D.d_idx.p, h->stream));
+    h->launches += D.n_eval ? 1 : 0;
+    D.idx_valid = true;
+    return DIND_OK;
+}
+
+template <typename T>
+int ensure_table(dind_interp_s* h, int dim, int order) {
+    DimState& D = h->dims[dim];
+    if (D.table.order == order) return DIND_OK;
+    CUDA_TRY(D.table.i0.ensure((size_t)D.n_eval * sizeof(int32_t)));
+    CUDA_TRY(D.table.w.ensure((size_t)D.n_eval * D.width * sizeof(T)));
+    CUDA_TRY(D.table.flag.ensure((size_t)D.n_eval));
+    DimParams<T> P = make_dim_params<T>(h, D, dim, order);
+    CUDA_TRY(launch_axis_table<T>(P, order, (int32_t*)D.table.i0.p, (T*)D.table.w.p, (uint8_t*)D.table.flag.p, h->stream));
+    h->launches += D.n_eval ? 1 : 0;
+    D.table.order = order;
+    return DIND_OK;
+}
+
+// validate_size_u / validate_cache (src/interpolation_utils.jl:39-63)
+int validate_interp(dind_interp_s* h) {
+    for (int d = 0; d < h->n_in; ++d)
+        if (!h->dims[d].set) return fail(DIND_ERR_STATE, "interpolation dimension %d has not been set (dind_set_dim)", d);
+    if (!h->u_set) return fail(DIND_ERR_STATE, "u has not been set (dind_set_u)");
+    for (int d = 0; d < h->n_in; ++d)
+        if (h->u_dims[d] != h->dims[d].n_u)
+            return fail(DIND_ERR_SIZE_MISMATCH,
+                        h->dims[d].kind == BSPLINE
+                            ? "Expected size(u, %d) == %lld based on the BSplineInterpolation properties, got %lld."
+                            : "For the first N_in dimensions of u the length must match the t of the corresponding interpolation dimension (dim %d: expected %lld, got %lld).",
+                        d + 1, (long long)h->dims[d].n_u, (long long)h->u_dims[d]);
+    if (h->w_set)
+        for (int d = 0; d < h->n_in; ++d)
+            if (h->dims[d].kind != BSPLINE)
+                return fail(DIND_ERR_INVALID_ARGUMENT, "NURBS weights need BSpline interpolation dimensions (dimension %d is not)", d + 1);
+    return DIND_OK;
+}
+
+// validate_derivative_orders (src/interpolation_utils.jl:5-32)
+int validate_orders(dind_interp_s* h, const int* orders_in, bool multi_point, int* orders) {
+    for (int d = 0; d < h->n_in; ++d) {
+        orders[d] = orders_in ? orders_in[d] : 0;
+        if (orders[d] < 0) return fail(DIND_ERR_INVALID_ARGUMENT, "Derivative orders must me non-negative.");
+    }
+    if (multi_point)
+        for (int d = 0; d < h->n_in; ++d)
+            if (h->dims[d].kind == BSPLINE && orders[d] > h->dims[d].max_deriv)
+                return fail(DIND_ERR_INVALID_ARGUMENT,
+                            "For BSpline interpolation, when using multi-point evaluation the derivative orders cannot be larger "
+                            "than the `max_derivative_order_eval` of the `BSplineInterpolationDimension` (dimension %d: %d > %d).",
+                            d + 1, orders[d], h->dims[d].max_deriv);
+    if (h->w_set)
+        for (int d = 0; d < h->n_in; ++d)
+            if (orders[d] != 0) return fail(DIND_ERR_INVALID_ARGUMENT, "Currently partial derivatives of NURBS are not supported.");
+    return DIND_OK;
+}
+
+template <typename T>
+int ensure_premultiplied(dind_interp_s* h) {
+    if (!h->w_set || h->uw_valid) return DIND_OK;
+    const int64_t n = h->comp_stride;
+    CUDA_TRY(h->uw.ensure((size_t)n * h->n_comp * sizeof(T)));
+    CUDA_TRY(launch_premultiply<T>((const T*)h->d_u, (const T*)h->d_w, (T*)h->uw.p, n, (int)h->n_comp, h->stream));
+    h->launches += 1;
+    h->uw_valid = true;
+    return DIND_OK;
+}
+
+// Common evaluation driver.  t_ptrs: device pointers to the per-dimension evaluation points.
+template <typename T>
+int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const void* const* t_dev,
+             const int64_t* n_eval, bool have_idx_cache, unsigned flags) {
+    const int N = h->n_in;
+    int64_t n_points = 1;
+    if (grid) for (int d = 0; d < N; ++d) n_points *= n_eval[d];
+    else n_points = n_eval[0];
+    if (n_points == 0) return DIND_OK;
+
+    int rc = ensure_premultiplied<T>(h);
+    if (rc) return rc;
+
+    EvalParams<T> P;
+    memset(&P, 0, sizeof P);
+    bool const_deriv = false, zero_result = false;
+    for (int d = 0; d < N; ++d) {
+        DimState& D = h->dims[d];
+        if (grid) {
+            rc = ensure_table<T>(h, d, orders[d]);
+            if (rc) return rc;
+        }
+        P.dim[d] = make_dim_params<T>(h, D, d, orders[d]);
+        P.dim[d].t_eval = (const T*)t_dev[d];
+        P.dim[d].n_eval = n_eval[d];
+        if (!have_idx_cache) P.dim[d].idx_eval = nullptr;
+        if (D.kind == CONSTANT && orders[d] > 0) const_deriv = true;
+        if (D.kind == LINEAR && orders[d] > 1) zero_result = true;
+    }
+    const bool out_on_device = is_device_ptr(out);
+    if ((flags & DIND_FLAG_ASYNC) && !out_on_device)
+        return fail(DIND_ERR_INVALID_ARGUMENT, "DIND_FLAG_ASYNC needs a device `out` pointer");
+    const size_t out_bytes = (size_t)n_points * h->n_comp * sizeof(T);
+    T* d_out = (T*)out;
+    const bool untouched_semantics = const_deriv && h->u_dims.size() > (size_t)N;
+    if (!out_on_device) {
+        CUDA_TRY(h->out_stage.ensure(out_bytes));
+        d_out = (T*)h->out_stage.p;
+        // Constant-with-derivative leaves vector outputs untouched off the knots
+        // (src/interpolation_methods.jl:49-55): keep the caller's values.
+        if (untouched_semantics) CUDA_TRY(cudaMemcpyAsync(d_out, out, out_bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    P.u = h->w_set ? (const T*)h->uw.p : (const T*)h->d_u;
+    P.wts = h->w_set ? (const T*)h->d_w : nullptr;
+    P.out = d_out;
+    P.n_points = n_points;
+    P.u_comp_stride = h->comp_stride;
+    P.out_comp_stride = n_points;
+    P.n_comp = (int32_t)h->n_comp;
+    P.n_in = N;
+    P.scalar_out = h->u_dims.size() == (size_t)N;
+    P.const_deriv = const_deriv;
+    P.zero_result = zero_result;
+    P.use_cached_idx = (!grid && have_idx_cache && (flags & DIND_FLAG_CACHED_IDX)) ? 1 : 0;
+    if (P.use_cached_idx) {
+        for (int d = 0; d < N; ++d) {
+            rc = ensure_idx<T>(h, d);
+            if (rc) return rc;
+            P.dim[d].idx_eval = (const int32_t*)h->dims[d].d_idx.p;
+        }
+    }
+
+    bool handled = false;
+    cudaError_t err = cudaSuccess;
+    const char* name = nullptr;
+    int nlaunch = 0;
+    if (!(flags & DIND_FLAG_GENERIC) && !const_deriv && !zero_result) {
+        handled = grid ? try_eval_fast_grid<T>(P, h->stream, &name, &err, &nlaunch)
+                       : try_eval_fast_unstructured<T>(P, h->stream, &name, &err, &nlaunch);
+    }
+    if (!handled) {
+        err = launch_eval_generic<T>(P, grid, h->stream);
+        name = grid ? "generic_grid" : "generic_unstructured";
+        nlaunch = 1;
+    }
+    CUDA_TRY(err);
+    h->last_kernel = name;
+    h->launches += nlaunch;
+    if (!out_on_device) {
+        CUDA_TRY(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    } else if (!(flags & DIND_FLAG_ASYNC)) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    return DIND_OK;
+}
+
+template <typename T>
+int eval_cached(dind_interp_s* h, void* out, const int* orders_in, bool grid, unsigned flags) {
+    int rc = validate_interp(h);
+    if (rc) return rc;
+    int orders[MAXN];
+    rc = validate_orders(h, orders_in, true, orders);
+    if (rc) return rc;
+    const void* t_dev[MAXN];
+    int64_t n_eval[MAXN];
+    for (int d = 0; d < h->n_in; ++d) {
+        if (!h->dims[d].teval_set) return fail(DIND_ERR_STATE, "t_eval of dimension %d has not been set (dind_set_t_eval)", d + 1);
+        t_dev[d] = h->dims[d].d_teval;
+        n_eval[d] = h->dims[d].n_eval;
+    }
+    if (!grid)
+        for (int d = 1; d < h->n_in; ++d)
+            if (n_eval[d] != n_eval[0])
+                return fail(DIND_ERR_SIZE_MISMATCH, "The t_eval of all interpolation dimensions must have the same length as the first dimension of out.");
+    if (!out) return fail(DIND_ERR_INVALID_ARGUMENT, "out is NULL");
+    return run_eval<T>(h, out, orders, grid, t_dev, n_eval, true, flags);
+}
+
+template <typename T>
+int eval_points(dind_interp_s* h, void* out, const void* const* t, int64_t n, const int* orders_in, unsigned flags) {
+    int rc = validate_interp(h);
+    if (rc) return rc;
+    int orders[MAXN];
+    rc = validate_orders(h, orders_in, false, orders);   // uncached call: no max_derivative_order_eval limit
+    if (rc) return rc;
+    if (n < 0) return fail(DIND_ERR_INVALID_ARGUMENT, "n must be non-negative");
+    if (!out || !t) return fail(DIND_ERR_INVALID_ARGUMENT, "out / t is NULL");
+    const void* t_dev[MAXN];
+    int64_t n_eval[MAXN];
+    for (int d = 0; d < h->n_in; ++d) {
+        if (!t[d]) return fail(DIND_ERR_INVALID_ARGUMENT, "t[%d] is NULL", d);
+        n_eval[d] = n;
+        if (is_device_ptr(t[d])) {
+            t_dev[d] = t[d];
+        } else {
+            CUDA_TRY(h->pts_stage[d].ensure((size_t)n * sizeof(T)));
+            CUDA_TRY(cudaMemcpyAsync(h->pts_stage[d].p, t[d], (size_t)n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+            t_dev[d] = h->pts_stage[d].p;
+        }
+    }
+    return run_eval<T>(h, out, orders, false, t_dev, n_eval, false, flags & ~DIND_FLAG_CACHED_IDX);
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+const char* dind_last_error(void) { return g_last_error.c_str(); }
+int dind_version(void) { return DIND_VERSION; }
+
+int dind_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int dind_create(dind_handle_t* handle, int n_in, int dtype, int device) {
+    if (!handle) return fail(DIND_ERR_INVALID_ARGUMENT, "handle pointer is NULL");
+    *handle = nullptr;
+    if (n_in < 1 || n_in > MAXN) return fail(DIND_ERR_UNSUPPORTED, "n_in must be in 1..%d, got %d", MAXN, n_in);
+    if (dtype != DIND_F32 && dtype != DIND_F64) return fail(DIND_ERR_UNSUPPORTED, "dtype must be DIND_F32 or DIND_F64");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(DIND_ERR_NO_DEVICE, "no CUDA device available (%s); libdind has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= ndev) return fail(DIND_ERR_INVALID_ARGUMENT, "device %d out of range 0..%d", device, ndev - 1);
+    CUDA_TRY(cudaSetDevice(device));
+    dind_interp_s* h = new dind_interp_s();
+    h->n_in = n_in;
+    h->dtype = dtype;
+    h->device = device;
+    h->esz = dtype == DIND_F32 ? 4 : 8;
+    *handle = h;
+    return DIND_OK;
+}
+
+int dind_destroy(dind_handle_t h) {
+    if (!h) return DIND_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int d = 0; d < MAXN; ++d) {
+        h->dims[d].release();
+        h->pts_stage[d].release();
+    }
+    h->u_owned.release(); h->w_owned.release(); h->uw.release(); h->out_stage.release();
+    delete h;
+    return DIND_OK;
+}
+
+int dind_set_stream(dind_handle_t h, void* cuda_stream) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    h->stream = (cudaStream_t)cuda_stream;
+    return DIND_OK;
+}
+
+int dind_synchronize(dind_handle_t h) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return DIND_OK;
+}
+
+int dind_set_dim(dind_handle_t h, int dim, int kind, const void* t, int64_t n_t, int degree,
+                 const int64_t* multiplicities, int left) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if ((rc = check_dim(h, dim))) return rc;
+    if (kind != DIND_LINEAR && kind != DIND_CONSTANT && kind != DIND_BSPLINE)
+        return fail(DIND_ERR_INVALID_ARGUMENT, "unknown interpolation dimension kind %d", kind);
+    if (!t || n_t < 1) return fail(DIND_ERR_INVALID_ARGUMENT, "t must hold at least one knot");
+    if (n_t > (1 << 24)) return fail(DIND_ERR_UNSUPPORTED, "more than 2^24 knots per dimension are not supported");
+    std::vector<double> tv((size_t)n_t);
+    std::vector<char> tmp;
+    const void* src = t;
+    if (is_device_ptr(t)) {
+        tmp.resize((size_t)n_t * h->esz);
+        CUDA_TRY(cudaMemcpy(tmp.data(), t, tmp.size(), cudaMemcpyDeviceToHost));
+        src = tmp.data();
+    }
+    for (int64_t i = 0; i < n_t; ++i) tv[i] = h->dtype == DIND_F32 ? (double)((const float*)src)[i] : ((const double*)src)[i];
+    // validate_t (src/interpolation_utils.jl:34-37): all(>(0), diff(t)) — NaN fails too
+    for (int64_t i = 1; i < n_t; ++i)
+        if (!(tv[i] - tv[i - 1] > 0)) return fail(DIND_ERR_INVALID_ARGUMENT, "The elements of t must be sorted and unique.");
+    if (std::isnan(tv[0])) return fail(DIND_ERR_INVALID_ARGUMENT, "The elements of t must be sorted and unique.");
+
+    DimState& D = h->dims[dim];
+    D.kind = kind;
+    D.left = left;
+    D.degree = 0;
+    D.t = tv;
+    D.mult.clear();
+    if (kind == DIND_BSPLINE) {
+        if (degree < 0) return fail(DIND_ERR_INVALID_ARGUMENT, "degree must be non-negative");
+        if (degree > DIND_MAX_DEGREE) return fail(DIND_ERR_UNSUPPORTED, "B-spline degree %d > %d is not supported", degree, DIND_MAX_DEGREE);
+        D.degree = degree;
+        if (multiplicities) D.mult.assign(multiplicities, multiplicities + n_t);
+        else {   // open/clamped knot vector (src/interpolation_dimensions.jl:168-173)
+            D.mult.assign((size_t)n_t, 1);
+            D.mult[0] = degree + 1;
+            D.mult[(size_t)n_t - 1] = degree + 1;
+        }
+        for (int64_t i = 0; i < n_t; ++i)   // :175
+            if (D.mult[i] < 1 || D.mult[i] > degree + 1) {
+                D.set = false;
+                return fail(DIND_ERR_INVALID_ARGUMENT, "All multiplicities must be between 1 and degree + 1.");
+            }
+        D.knots.clear();
+        for (int64_t i = 0; i < n_t; ++i)   // expand_knot_vector_kernel (src/spline_utils.jl:1-20)
+            for (int64_t m = 0; m < D.mult[i]; ++m) D.knots.push_back(tv[i]);
+        D.width = degree + 1;
+        D.n_u = (int64_t)D.knots.size() - degree - 1;   // get_n_basis_functions (:223-225)
+        if (D.n_u < degree + 1) {
+            D.set = false;
+            return fail(DIND_ERR_INVALID_ARGUMENT, "knot vector too short for degree %d (%lld basis functions)", degree, (long long)D.n_u);
+        }
+    } else {
+        if (n_t < 2) return fail(DIND_ERR_INVALID_ARGUMENT, "Linear/Constant dimensions need at least 2 knots");
+        D.knots = tv;
+        D.width = kind == DIND_LINEAR ? 2 : 1;
+        D.n_u = n_t;
+    }
+    rc = h->dtype == DIND_F32 ? upload_dim<float>(h, D) : upload_dim<double>(h, D);
+    if (rc) return rc;
+    D.set = true;
+    D.invalidate_caches();
+    return DIND_OK;
+}
+
+int dind_set_t_eval(dind_handle_t h, int dim, const void* t_eval, int64_t n_eval, int max_derivative_order_eval,
+                    unsigned flags) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if ((rc = check_dim(h, dim))) return rc;
+    if (n_eval < 0) return fail(DIND_ERR_INVALID_ARGUMENT, "n_eval must be non-negative");
+    if (n_eval > 0 && !t_eval) return fail(DIND_ERR_INVALID_ARGUMENT, "t_eval is NULL");
+    if (max_derivative_order_eval < 0) return fail(DIND_ERR_INVALID_ARGUMENT, "max_derivative_order_eval must be non-negative");
+    DimState& D = h->dims[dim];
+    const size_t bytes = (size_t)n_eval * h->esz;
+    if (n_eval > 0 && is_device_ptr(t_eval) && !(flags & DIND_FLAG_COPY)) {
+        D.d_teval = t_eval;   // borrowed
+    } else {
+        CUDA_TRY(D.teval_owned.ensure(bytes));
+        if (n_eval > 0)
+            CUDA_TRY(cudaMemcpyAsync(D.teval_owned.p, t_eval, bytes,
+                                     is_device_ptr(t_eval) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        D.d_teval = D.teval_owned.p;
+    }
+    D.n_eval = n_eval;
+    D.max_deriv = max_derivative_order_eval;
+    D.teval_set = true;
+    D.invalidate_caches();
+    return DIND_OK;
+}
+
+int dind_set_u(dind_handle_t h, const void* u, const int64_t* dims, int ndims, unsigned flags) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!u || !dims) return fail(DIND_ERR_INVALID_ARGUMENT, "u / dims is NULL");
+    if (ndims < h->n_in)   // src/DataInterpolationsND.jl:44
+        return fail(DIND_ERR_SIZE_MISMATCH, "The number of dimensions of u must be at least the number of interpolation dimensions.");
+    int64_t comp_stride = 1, n_comp = 1;
+    for (int i = 0; i < ndims; ++i) {
+        if (dims[i] < 1) return fail(DIND_ERR_SIZE_MISMATCH, "size(u, %d) must be positive", i + 1);
+        if (i < h->n_in) comp_stride *= dims[i]; else n_comp *= dims[i];
+    }
+    if (n_comp > (1 << 20)) return fail(DIND_ERR_UNSUPPORTED, "more than 2^20 output components are not supported");
+    for (int d = 0; d < h->n_in; ++d)
+        if (h->dims[d].set && dims[d] != h->dims[d].n_u)
+            return fail(DIND_ERR_SIZE_MISMATCH, "size(u, %d) is %lld, the interpolation dimension expects %lld.", d + 1,
+                        (long long)dims[d], (long long)h->dims[d].n_u);
+    if (h->w_set) {
+        int64_t wn = 1;
+        for (int d = 0; d < h->n_in; ++d) wn *= dims[d];
+        if (wn != h->comp_stride && h->u_set)
+            return fail(DIND_ERR_SIZE_MISMATCH, "size(u)[1:N_in] changed while NURBS weights are set; reset the weights first");
+    }
+    const size_t bytes = (size_t)comp_stride * n_comp * h->esz;
+    if (is_device_ptr(u) && !(flags & DIND_FLAG_COPY)) {
+        h->d_u = u;   // borrowed
+    } else {
+        CUDA_TRY(h->u_owned.ensure(bytes));
+        CUDA_TRY(cudaMemcpyAsync(h->u_owned.p, u, bytes, is_device_ptr(u) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+        if (!is_device_ptr(u)) CUDA_TRY(cudaStreamSynchronize(h->stream));   // pageable source may be reused by the caller
+        h->d_u = h->u_owned.p;
+    }
+    h->u_dims.assign(dims, dims + ndims);
+    h->comp_stride = comp_stride;
+    h->n_comp = n_comp;
+    h->u_set = true;
+    h->uw_valid = false;
+    return DIND_OK;
+}
+
+int dind_set_weights(dind_handle_t h, const void* weights, const int64_t* dims, int ndims, unsigned flags) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    h->uw_valid = false;
+    if (!weights) {
+        h->w_set = false;
+        h->d_w = nullptr;
+        return DIND_OK;
+    }
+    if (!dims || ndims != h->n_in)
+        return fail(DIND_ERR_SIZE_MISMATCH, "The size of the weights array must match the length of the first N_in dimensions of u.");
+    int64_t n = 1;
+    for (int d = 0; d < ndims; ++d) {
+        if (h->u_set && dims[d] != h->u_dims[d])   // validate_cache (src/interpolation_utils.jl:56-63)
+            return fail(DIND_ERR_SIZE_MISMATCH, "The size of the weights array must match the length of the first N_in dimensions of u.");
+        if (h->dims[d].set && dims[d] != h->dims[d].n_u)
+            return fail(DIND_ERR_SIZE_MISMATCH, "size(weights, %d) is %lld, the interpolation dimension expects %lld.", d + 1,
+                        (long long)dims[d], (long long)h->dims[d].n_u);
+        n *= dims[d];
+    }
+    const size_t bytes = (size_t)n * h->esz;
+    if (is_device_ptr(weights) && !(flags & DIND_FLAG_COPY)) {
+        h->d_w = weights;
+    } else {
+        CUDA_TRY(h->w_owned.ensure(bytes));
+        CUDA_TRY(cudaMemcpyAsync(h->w_owned.p, weights, bytes, is_device_ptr(weights) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+        if (!is_device_ptr(weights)) CUDA_TRY(cudaStreamSynchronize(h->stream));
+        h->d_w = h->w_owned.p;
+    }
+    h->w_set = true;
+    return DIND_OK;
+}
+
+int dind_eval_unstructured(dind_handle_t h, void* out, const int* derivative_orders, unsigned flags) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    return h->dtype == DIND_F32 ? eval_cached<float>(h, out, derivative_orders, false, flags)
+                                : eval_cached<double>(h, out, derivative_orders, false, flags);
+}
+
+int dind_eval_grid(dind_handle_t h, void* out, const int* derivative_orders, unsigned flags) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    return h->dtype == DIND_F32 ? eval_cached<float>(h, out, derivative_orders, true, flags)
+                                : eval_cached<double>(h, out, derivative_orders, true, flags);
+}
+
+int dind_eval_points(dind_handle_t h, void* out, const void* const* t, int64_t n, const int* derivative_orders,
+                     unsigned flags) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    return h->dtype == DIND_F32 ? eval_points<float>(h, out, t, n, derivative_orders, flags)
+                                : eval_points<double>(h, out, t, n, derivative_orders, flags);
+}
+
+int dind_get_idx_eval(dind_handle_t h, int dim, int64_t* idx_out) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if ((rc = check_dim(h, dim))) return rc;
+    DimState& D = h->dims[dim];
+    if (!D.set || !D.teval_set) return fail(DIND_ERR_STATE, "dimension %d needs dind_set_dim and dind_set_t_eval first", dim + 1);
+    if (D.n_eval == 0) return DIND_OK;
+    if (!idx_out) return fail(DIND_ERR_INVALID_ARGUMENT, "idx_out is NULL");
+    rc = h->dtype == DIND_F32 ? ensure_idx<float>(h, dim) : ensure_idx<double>(h, dim);
+    if (rc) return rc;
+    std::vector<int32_t> tmp((size_t)D.n_eval);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), D.d_idx.p, tmp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int64_t i = 0; i < D.n_eval; ++i) idx_out[i] = tmp[i];
+    return DIND_OK;
+}
+
+int dind_get_knots_all(dind_handle_t h, int dim, void* knots_out, int64_t* n_out) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if ((rc = check_dim(h, dim))) return rc;
+    DimState& D = h->dims[dim];
+    if (!D.set) return fail(DIND_ERR_STATE, "dimension %d has not been set", dim + 1);
+    if (n_out) *n_out = (int64_t)D.knots.size();
+    if (knots_out)
+        for (size_t i = 0; i < D.knots.size(); ++i) {
+            if (h->dtype == DIND_F32) ((float*)knots_out)[i] = (float)D.knots[i];
+            else ((double*)knots_out)[i] = D.knots[i];
+        }
+    return DIND_OK;
+}
+
+int dind_get_basis_function_eval(dind_handle_t h, int dim, void* basis_out) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if ((rc = check_dim(h, dim))) return rc;
+    DimState& D = h->dims[dim];
+    if (!D.set || !D.teval_set) return fail(DIND_ERR_STATE, "dimension %d needs dind_set_dim and dind_set_t_eval first", dim + 1);
+    if (D.kind != BSPLINE) return fail(DIND_ERR_INVALID_ARGUMENT, "dimension %d is not a BSpline dimension", dim + 1);
+    if (D.n_eval == 0) return DIND_OK;
+    if (!basis_out) return fail(DIND_ERR_INVALID_ARGUMENT, "basis_out is NULL");
+    const size_t count = (size_t)D.n_eval * (D.degree + 1) * (D.max_deriv + 1);
+    DevBuf tmp;
+    CUDA_TRY(tmp.ensure(count * h->esz));
+    cudaError_t e;
+    if (h->dtype == DIND_F32) e = launch_basis_cache<float>(make_dim_params<float>(h, D, dim, 0), D.max_deriv, (float*)tmp.p, h->stream);
+    else e = launch_basis_cache<double>(make_dim_params<double>(h, D, dim, 0), D.max_deriv, (double*)tmp.p, h->stream);
+    h->launches += 1;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(basis_out, tmp.p, count * h->esz, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    tmp.release();
+    CUDA_TRY(e);
+    return DIND_OK;
+}
+
+const char* dind_last_kernel(dind_handle_t h) { return h ? h->last_kernel.c_str() : "none"; }
+int64_t dind_launch_count(dind_handle_t h) { return h ? h->launches : 0; }
+
+int dind_shard_range(int64_t n, int rank, int world, int64_t* lo, int64_t* hi) {
+    if (world < 1 || rank < 0 || rank >= world || n < 0 || !lo || !hi)
+        return fail(DIND_ERR_INVALID_ARGUMENT, "bad shard arguments (n=%lld rank=%d world=%d)", (long long)n, rank, world);
+    const int64_t q = n / world, r = n % world;
+    *lo = rank * q + (rank < r ? rank : r);
+    *hi = *lo + q + (rank < r ? 1 : 0);
+    return DIND_OK;
+}
+
+int dind_host_register(void* ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return fail(DIND_ERR_INVALID_ARGUMENT, "bad host_register arguments");
+    CUDA_TRY(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return DIND_OK;
+}
+
+int dind_host_unregister(void* ptr) {
+    if (!ptr) return fail(DIND_ERR_INVALID_ARGUMENT, "ptr is NULL");
+    CUDA_TRY(cudaHostUnregister(ptr));
+    return DIND_OK;
+}
+
+}  // extern "C"

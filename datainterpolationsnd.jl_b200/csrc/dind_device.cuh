@@ -1,0 +1,217 @@
+// dind_device.cuh — device-side building blocks shared by all kernels of libdind.so.
+//
+// Restates, for the GPU, the per-point math of the reference:
+//   interval search  : src/interpolation_utils.jl:104-134 (get_idx) on Base.searchsortedfirst/last
+//   Cox–de Boor basis: src/spline_utils.jl:22-114
+//   stencils         : src/interpolation_methods.jl:1-141
+// B200 notes: everything here is register/shared-memory math feeding HBM/L2-bound gathers;
+// no tensor-core work (per-axis bands are 2..8 wide).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+namespace dind {
+
+constexpr int MAXN = 8;  // DIND_MAX_DIMS
+constexpr int MAXW = 8;  // DIND_MAX_DEGREE + 1
+
+enum Kind : int { LINEAR = 0, CONSTANT = 1, BSPLINE = 2 };
+
+// ---- Julia `isless` total order via sortable integer keys -------------------------------
+// key(a) < key(b)  <=>  isless(a, b):  -0.0 < +0.0, every NaN is the greatest element.
+template <typename T> struct KeyOf;
+template <> struct KeyOf<float> { using type = int32_t; };
+template <> struct KeyOf<double> { using type = int64_t; };
+
+__host__ __device__ __forceinline__ int32_t to_key(float v) {
+#ifdef __CUDA_ARCH__
+    int32_t b = __float_as_int(v);
+#else
+    int32_t b; memcpy(&b, &v, 4);
+#endif
+    if ((b & 0x7fffffff) > 0x7f800000) return 0x7fffffff;  // NaN (either sign) sorts last
+    return b ^ ((b >> 31) & 0x7fffffff);
+}
+__host__ __device__ __forceinline__ int64_t to_key(double v) {
+#ifdef __CUDA_ARCH__
+    int64_t b = __double_as_longlong(v);
+#else
+    int64_t b; memcpy(&b, &v, 8);
+#endif
+    if ((b & 0x7fffffffffffffffLL) > 0x7ff0000000000000LL) return 0x7fffffffffffffffLL;
+    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+
+// Number of keys <= kx (searchsortedlast) / < kx (searchsortedfirst - 1) in a sorted array.
+// Branch-free binary lifting: ceil(log2(n+1)) predicated steps, no divergence.
+template <typename K>
+__device__ __forceinline__ int count_le(const K* __restrict__ keys, int n, K kx) {
+    int lo = 0;
+    int step = 1 << (31 - __clz(n | 1));
+    for (; step > 0; step >>= 1) {
+        int j = lo + step;
+        if (j <= n && keys[j - 1] <= kx) lo = j;
+    }
+    return lo;
+}
+template <typename K>
+__device__ __forceinline__ int count_lt(const K* __restrict__ keys, int n, K kx) {
+    int lo = 0;
+    int step = 1 << (31 - __clz(n | 1));
+    for (; step > 0; step >>= 1) {
+        int j = lo + step;
+        if (j <= n && keys[j - 1] < kx) lo = j;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int clampi(int x, int lo, int hi) { return x > hi ? hi : (x < lo ? lo : x); }
+
+// ---- per-dimension device descriptor ------------------------------------------------------
+template <typename T>
+struct DimParams {
+    using K = typename KeyOf<T>::type;
+    const T* knots;        // t (Linear/Constant) or knots_all (BSpline)
+    const K* keys;         // to_key(knots)
+    const T* recip;        // Linear: 1/(t[c+1]-t[c]), n_knots-1 entries
+                           // BSpline: R_d[i] = safe 1/(K[i+d]-K[i]), layout [(d-1)*n_knots + i]
+    const T* t_eval;       // unstructured: per point; grid: per axis
+    const int32_t* idx_eval;  // optional cache of the reference's 1-based idx_eval
+    // per-axis tables for grid evaluation (built for the requested derivative order)
+    const int32_t* tab_i0;    // first stencil node (0-based) per grid coordinate
+    const T* tab_w;           // weights [g * width + a]
+    const uint8_t* tab_flag;  // bit0: Constant-with-derivative on a knot
+    int64_t n_eval;
+    int64_t u_stride;      // element stride of this dimension in u
+    int32_t n_knots;
+    int32_t kind;
+    int32_t degree;
+    int32_t width;         // stencil width: 1 Constant, 2 Linear, degree+1 BSpline
+    int32_t n_u;           // size(u, dim)
+    int32_t order;         // derivative order requested for this dimension
+};
+
+template <typename T>
+struct EvalParams {
+    DimParams<T> dim[MAXN];
+    const T* u;            // (n_1..n_N, comps): NURBS: pre-multiplied by the weights
+    const T* wts;          // NURBS weights (n_1..n_N) or null
+    T* out;                // (n_points, comps)
+    int64_t n_points;
+    int64_t u_comp_stride;
+    int64_t out_comp_stride;
+    int32_t n_comp;
+    int32_t n_in;
+    int32_t scalar_out;    // N_out == 0
+    int32_t const_deriv;   // some Constant dimension has derivative order > 0
+    int32_t zero_result;   // Linear with order > 1 somewhere: result is identically zero
+    int32_t use_cached_idx;
+};
+
+// ---- Cox–de Boor in registers (src/spline_utils.jl:24-114), runtime degree ---------------
+// idx0: 0-based knot interval (reference idx - 1).  Writes p+1 values to w[0..p].
+// Division by the knot spans is replaced by the precomputed safe reciprocals R_d[i]
+// (safe_div(a, 0) = 0 of spline_utils.jl:22 <=> R = 0).
+template <typename T>
+__device__ __forceinline__ void bspline_basis_rt(const T* __restrict__ Kn, const T* __restrict__ R, int nk,
+                                                 int p, int idx0, T x, int order, T* w) {
+    if (order > p) {                       // :79-81
+        for (int s = 0; s <= p; ++s) w[s] = T(0);
+        return;
+    }
+    T b[MAXW + 1];
+    for (int s = 0; s <= p + 1; ++s) b[s] = (s == p) ? T(1) : T(0);   // :86-89
+    for (int d = 1; d <= p; ++d) {         // :104-112
+        const bool deriv = d > p - order;  // :105
+        const T* Rd = R + (int64_t)(d - 1) * nk;
+        for (int s = p - d; s <= p; ++s) { // slots below p-d stay zero (:33-34)
+            const int i = idx0 - p + s;
+            T v;
+            if (deriv) v = T(d) * (b[s] * Rd[i] - b[s + 1] * Rd[i + 1]);               // :38-41
+            else v = b[s] * ((x - Kn[i]) * Rd[i]) + b[s + 1] * ((Kn[i + d + 1] - x) * Rd[i + 1]);  // :45-46
+            b[s] = v;                      // in place: b[s+1] is still the previous stage's value
+        }
+    }
+    for (int s = 0; s <= p; ++s) w[s] = b[s];   // :97
+}
+
+// Compile-time degree version for the specialised kernels: fully unrolled, knots of the
+// 2P+2 wide window are read once.
+template <typename T, int P>
+__device__ __forceinline__ void bspline_basis_ct(const T* __restrict__ Kn, const T* __restrict__ R, int nk,
+                                                 int idx0, T x, int order, T (&w)[P + 1]) {
+    if (order > P) {
+#pragma unroll
+        for (int s = 0; s <= P; ++s) w[s] = T(0);
+        return;
+    }
+    T kn[2 * P + 2];                        // kn[j] = K[idx0 - P + j]
+#pragma unroll
+    for (int j = 0; j < 2 * P + 2; ++j) kn[j] = Kn[idx0 - P + j];
+    T b[P + 2];
+#pragma unroll
+    for (int s = 0; s <= P + 1; ++s) b[s] = (s == P) ? T(1) : T(0);
+#pragma unroll
+    for (int d = 1; d <= P; ++d) {
+        const bool deriv = d > P - order;
+        const T* Rd = R + (d - 1) * nk + (idx0 - P);
+#pragma unroll
+        for (int s = P - d; s <= P; ++s) {
+            // R_d at i = idx0-P+s and i+1; the lowest slot only needs the second term
+            // (b[P-d] is zero on entry), the top slot only the first (b[P+1] == 0).
+            T v;
+            if (deriv) {
+                T a = (s > P - d) ? b[s] * Rd[s] : T(0);
+                T c = (s < P) ? b[s + 1] * Rd[s + 1] : T(0);
+                v = T(d) * (a - c);
+            } else {
+                T a = (s > P - d) ? b[s] * ((x - kn[s]) * Rd[s]) : T(0);
+                T c = (s < P) ? b[s + 1] * ((kn[s + d + 1] - x) * Rd[s + 1]) : T(0);
+                v = a + c;
+            }
+            b[s] = v;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s <= P; ++s) w[s] = b[s];
+}
+
+// ---- one dimension's stencil: first node, weights, flags ------------------------------------
+// cached_idx: the reference's 1-based idx_eval value, or 0 to search here.
+// Returns the reference's 1-based idx through idx1 (for the idx cache kernels).
+template <typename T>
+__device__ __forceinline__ void dim_stencil(const DimParams<T>& D, T x, int order, int cached_idx,
+                                            int& i0, T* w, bool& on_knot, int& idx1) {
+    using K = typename KeyOf<T>::type;
+    const K kx = to_key(x);
+    const int n = D.n_knots;
+    on_knot = false;
+    if (D.kind == LINEAR) {
+        // clamp(searchsortedfirst(t, x) - 1, 1, n-1): intervals (t[i], t[i+1]]
+        const int idx = cached_idx ? cached_idx : clampi(count_lt(D.keys, n, kx), 1, n - 1);
+        idx1 = idx;
+        const int c = idx - 1;
+        const T t1 = D.knots[c], t2 = D.knots[c + 1], r = D.recip[c];
+        i0 = c;
+        if (order == 0) { w[0] = (t2 - x) * r; w[1] = (x - t1) * r; }       // interpolation_methods.jl:24-30
+        else if (order == 1) { w[0] = -r; w[1] = r; }
+        else { w[0] = T(0); w[1] = T(0); }                                  // :10
+    } else if (D.kind == CONSTANT) {
+        // clamp(searchsortedlast(t, x), 1, n-1): intervals [t[i], t[i+1])
+        const int cnt = count_le(D.keys, n, kx);
+        const int idx = cached_idx ? cached_idx : clampi(cnt, 1, n - 1);
+        idx1 = idx;
+        i0 = (x >= D.knots[n - 1]) ? n - 1 : idx - 1;                       // :57-59
+        w[0] = T(1);
+        if (order > 0) on_knot = count_lt(D.keys, n, kx) < cnt;             // :50 !isempty(searchsorted(t, x))
+    } else {
+        const int p = D.degree;
+        const int idx = cached_idx ? cached_idx : clampi(count_le(D.keys, n, kx), p + 1, n - p - 1);
+        idx1 = idx;
+        i0 = idx - p - 1;                                                   // :87-89
+        bspline_basis_rt<T>(D.knots, D.recip, n, p, idx - 1, x, order, w);
+    }
+}
+
+}  // namespace dind

@@ -1,0 +1,27 @@
+// dind_kernels.h — host-callable launchers of the CUDA kernels (one explicit instantiation per
+// element type in the .cu that defines them).
+#pragma once
+#include "dind_device.cuh"
+
+namespace dind {
+
+// set_idx_kernel (src/interpolation_utils.jl:156-161): idx_out[i] = get_idx(dim, t_eval[i]), 1-based.
+template <typename T> cudaError_t launch_idx(const DimParams<T>& D, int32_t* idx_out, cudaStream_t s);
+// basis_function_eval_kernel (src/spline_utils.jl:174-191): out[(i, k, r)] column-major.
+template <typename T> cudaError_t launch_basis_cache(const DimParams<T>& D, int max_deriv, T* out, cudaStream_t s);
+// per-axis stencil tables for grid evaluation at one derivative order.
+template <typename T> cudaError_t launch_axis_table(const DimParams<T>& D, int order, int32_t* tab_i0, T* tab_w,
+                                                    uint8_t* tab_flag, cudaStream_t s);
+// uw[i + c*n] = u[i + c*n] * w[i]  (NURBS numerator, src/interpolation_methods.jl:124-131)
+template <typename T> cudaError_t launch_premultiply(const T* u, const T* w, T* uw, int64_t n, int n_comp, cudaStream_t s);
+// generic evaluation: any N_in <= MAXN, any kinds, any degree <= MAXW-1
+template <typename T> cudaError_t launch_eval_generic(const EvalParams<T>& P, bool grid, cudaStream_t s);
+
+// Specialised kernels.  Return true when they handled the evaluation (err holds the launch
+// status), false when the configuration is outside their envelope.
+template <typename T> bool try_eval_fast_unstructured(const EvalParams<T>& P, cudaStream_t s, const char** name,
+                                                      cudaError_t* err, int* launches);
+template <typename T> bool try_eval_fast_grid(const EvalParams<T>& P, cudaStream_t s, const char** name,
+                                              cudaError_t* err, int* launches);
+
+}  // namespace dind

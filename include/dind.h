@@ -1,0 +1,164 @@
+/* dind.h — C ABI of libdind.so: B200 (sm_100a) evaluation engine for the batched
+ * evaluation hot path of DataInterpolationsND.jl.
+ *
+ * This header is the drop-in boundary.  The reference has no FFI: its seam
+ * is Julia dispatch on the KernelAbstractions backend (`get_backend(out)` followed by
+ * `synchronize(backend)`, src/interpolation_parallel.jl:40-50, :91-101) and
+ * `Adapt.adapt_structure` as the host->device hook (src/DataInterpolationsND.jl:58-64).
+ * A Julia host package `ccall`s the functions below instead (see INTEGRATION.md for the
+ * binding); the Python package in datainterpolationsnd.jl_b200/ binds the same symbols with
+ * ctypes.  Each entry point names the reference interface it replaces (paths relative to
+ * the reference repository root).
+ *
+ * Conventions
+ *  - Plain C types only; opaque handle; no exceptions cross the boundary.
+ *  - Every function returns an int status: DIND_OK (0) or a negative DIND_ERR_* code;
+ *    dind_last_error() returns a thread-local, human-readable message for the last failure
+ *    on the calling thread.  The reference raises AssertionError (`@assert`) for every
+ *    validation failure; the host wrapper turns a negative status into that exception.
+ *  - Arrays are column-major (Julia): `u` is (n_1..n_N, out...), `out` is
+ *    (n_points, out...) / (g_1..g_N, out...), element type = element type of `u`.
+ *  - A data pointer may be a HOST pointer (pageable or pinned) or a DEVICE pointer of the
+ *    handle's device; the library detects which (cudaPointerGetAttributes).  Host data is
+ *    copied; device data passed to dind_set_u / dind_set_t_eval / dind_set_weights is
+ *    BORROWED (zero-copy, the analogue of `adapt_structure` handing over a device array):
+ *    the caller keeps it alive and unchanged until it is replaced or the handle destroyed,
+ *    unless DIND_FLAG_COPY is given.
+ *  - All calls are synchronous like the reference's (each KA launch is followed by
+ *    `synchronize(backend)`) unless DIND_FLAG_ASYNC is passed with a device `out`.
+ *  - A handle may be used by one host thread at a time; distinct handles are independent.
+ *  - There is no CPU fallback: without a CUDA device dind_create fails with
+ *    DIND_ERR_NO_DEVICE.
+ */
+#ifndef DIND_H
+#define DIND_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIND_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define DIND_OK 0
+#define DIND_ERR_INVALID_ARGUMENT (-1) /* a reference `@assert` on values would have failed      */
+#define DIND_ERR_SIZE_MISMATCH (-2)    /* a reference `@assert` on sizes would have failed       */
+#define DIND_ERR_UNSUPPORTED (-3)      /* valid in the reference, not supported by this engine   */
+#define DIND_ERR_CUDA (-4)             /* CUDA runtime error, message has the CUDA error string  */
+#define DIND_ERR_STATE (-5)            /* call order: e.g. eval before set_u / set_t_eval        */
+#define DIND_ERR_NO_DEVICE (-6)        /* no usable CUDA device: there is no CPU fallback        */
+
+/* element types (eltype(u); knots, t_eval and out use the same type) */
+#define DIND_F32 0
+#define DIND_F64 1
+
+/* interpolation dimension kinds: src/interpolation_dimensions.jl:15, :61, :119 */
+#define DIND_LINEAR 0
+#define DIND_CONSTANT 1
+#define DIND_BSPLINE 2
+
+/* flags */
+#define DIND_FLAG_ASYNC 1u       /* do not wait for the stream before returning (device `out` only) */
+#define DIND_FLAG_COPY 2u        /* copy device data instead of borrowing it                           */
+#define DIND_FLAG_CACHED_IDX 4u  /* eval_unstructured: read the idx_eval cache instead of searching   */
+#define DIND_FLAG_GENERIC 8u     /* force the generic (any-N, any-degree) kernels; testing/reference  */
+#define DIND_FLAG_NO_SORT_CHECK 16u /* reserved */
+
+#define DIND_MAX_DIMS 8   /* N_in <= 8 */
+#define DIND_MAX_DEGREE 7 /* B-spline degree <= 7 */
+
+typedef struct dind_interp_s* dind_handle_t;
+
+/* ---- lifecycle --------------------------------------------------------------------------
+ * Replaces: NDInterpolation(u, interp_dims; cache) — src/DataInterpolationsND.jl:29-56 — as
+ * the owner of the device-resident state, and adapt_structure (:58-64) as the transfer hook.
+ * `device` is a CUDA ordinal (one process per GPU: pass LOCAL_RANK). */
+int dind_create(dind_handle_t* handle, int n_in, int dtype, int device);
+int dind_destroy(dind_handle_t handle);
+/* Use `cuda_stream` (a cudaStream_t; NULL = the legacy default stream) for every launch and copy. */
+int dind_set_stream(dind_handle_t handle, void* cuda_stream);
+int dind_synchronize(dind_handle_t handle);
+
+/* ---- per-dimension setup ----------------------------------------------------------------
+ * Replaces the dimension constructors LinearInterpolationDimension(t; t_eval),
+ * ConstantInterpolationDimension(t; left, t_eval), BSplineInterpolationDimension(t, degree;
+ * t_eval, max_derivative_order_eval, multiplicities) — src/interpolation_dimensions.jl:37-44,
+ * :87-94, :162-204 — including validate_t (src/interpolation_utils.jl:34-37), the default
+ * clamped multiplicities (:168-173), the multiplicity asserts (:174-175) and the knot
+ * expansion kernel (src/spline_utils.jl:1-20).
+ * `t`: n_t strictly increasing knots (host pointer). `degree`, `multiplicities` (host, n_t
+ * entries or NULL = clamped) only for DIND_BSPLINE. `left` is stored and, exactly like the
+ * reference's field (src/interpolation_dimensions.jl:67), never read by evaluation. */
+int dind_set_dim(dind_handle_t handle, int dim, int kind, const void* t, int64_t n_t, int degree,
+                 const int64_t* multiplicities, int left);
+
+/* Replaces the `t_eval` keyword of the constructors + set_eval_idx! / set_idx_kernel
+ * (src/interpolation_utils.jl:143-161) + set_basis_function_eval!
+ * (src/spline_utils.jl:164-191).  `t_eval`: host or device pointer, n_eval >= 0 points.
+ * The per-point index cache is built lazily on the device (dind_get_idx_eval, or evaluation
+ * with DIND_FLAG_CACHED_IDX); unstructured evaluation otherwise searches in-kernel and
+ * recomputes the basis in registers, grid evaluation uses small per-axis tables. */
+int dind_set_t_eval(dind_handle_t handle, int dim, const void* t_eval, int64_t n_eval,
+                    int max_derivative_order_eval, unsigned flags);
+
+/* ---- data -------------------------------------------------------------------------------
+ * Replaces the `u` argument of NDInterpolation and validate_size_u
+ * (src/interpolation_utils.jl:39-52).  dims[0..ndims-1] = size(u); ndims >= n_in.  Call again
+ * for every new `u` (cheap for device pointers: borrowed, plus one pre-multiply pass when
+ * NURBS weights are set). */
+int dind_set_u(dind_handle_t handle, const void* u, const int64_t* dims, int ndims, unsigned flags);
+/* Replaces NURBSWeights(weights) as `cache` + validate_cache (src/spline_utils.jl:232-234,
+ * src/interpolation_utils.jl:54-63).  weights == NULL removes them (EmptyCache). */
+int dind_set_weights(dind_handle_t handle, const void* weights, const int64_t* dims, int ndims,
+                     unsigned flags);
+
+/* ---- evaluation -------------------------------------------------------------------------
+ * derivative_orders: n_in non-negative ints (NULL = all zero), validated as
+ * validate_derivative_orders(...; multi_point = true) — src/interpolation_utils.jl:5-32.
+ * `out`: host or device pointer with room for n_points * prod(out dims) elements. */
+
+/* eval_unstructured!(out, interp; derivative_orders) — src/interpolation_parallel.jl:34-52. */
+int dind_eval_unstructured(dind_handle_t handle, void* out, const int* derivative_orders,
+                           unsigned flags);
+/* eval_grid!(out, interp; derivative_orders) — src/interpolation_parallel.jl:85-103. */
+int dind_eval_grid(dind_handle_t handle, void* out, const int* derivative_orders, unsigned flags);
+/* Batched form of the uncached in-place call interp(out, t...; derivative_orders) —
+ * src/DataInterpolationsND.jl:85-94: t[d] points to n values for dimension d (all host or all
+ * device); out is (n, out...).  Does not touch the handle's t_eval. */
+int dind_eval_points(dind_handle_t handle, void* out, const void* const* t, int64_t n,
+                     const int* derivative_orders, unsigned flags);
+
+/* ---- introspection (parity tests; fields the reference exposes on its structs) ---------- */
+/* idx_eval, 1-based Int64 exactly as the reference stores it (src/interpolation_dimensions.jl:38). */
+int dind_get_idx_eval(dind_handle_t handle, int dim, int64_t* idx_out /* host, n_eval */);
+/* knots_all of a BSpline dimension; n_out receives its length; knots_out may be NULL. */
+int dind_get_knots_all(dind_handle_t handle, int dim, void* knots_out /* host */, int64_t* n_out);
+/* basis_function_eval[n_eval, degree+1, max_derivative_order_eval+1] (column-major), computed
+ * on the device on demand (src/spline_utils.jl:174-191). */
+int dind_get_basis_function_eval(dind_handle_t handle, int dim, void* basis_out /* host */);
+/* Name of the kernel family the last evaluation on this handle dispatched to. */
+const char* dind_last_kernel(dind_handle_t handle);
+/* Number of kernel launches issued by this handle so far. */
+int64_t dind_launch_count(dind_handle_t handle);
+
+/* ---- multi-GPU helpers --------------------------------------------------------------------
+ * Sharding is by contiguous index range (unstructured points) or by slab along the last
+ * interpolation axis (grids); each rank creates its own handle over its slice of t_eval.
+ * [lo, hi) = the part of 0..n-1 owned by `rank` of `world`; ranges differ by at most 1. */
+int dind_shard_range(int64_t n, int rank, int world, int64_t* lo, int64_t* hi);
+
+/* ---- pinned host memory (for the host-buffer path) ---------------------------------------- */
+int dind_host_register(void* ptr, int64_t bytes);
+int dind_host_unregister(void* ptr);
+
+/* ---- misc ---------------------------------------------------------------------------------- */
+const char* dind_last_error(void);
+int dind_version(void);
+int dind_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIND_H */

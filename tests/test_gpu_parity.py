@@ -1,0 +1,378 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every evaluation goes through the host
+mirror -> C ABI (libdind.so) -> CUDA kernels and is compared with the CPU oracle on the same
+seeded inputs; interval indices bit-exact, values within the north_star tolerances (helpers.TOL)."""
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+GENERIC = 8  # DIND_FLAG_GENERIC
+CACHED_IDX = 4
+
+
+@pytest.fixture(scope="module")
+def D():
+    import dind_b200
+    assert dind_b200._lib.load().dind_device_count() > 0, "no CUDA device: the GPU tests need a B200"
+    return dind_b200
+
+
+DTYPES = [np.float64, np.float32]
+
+
+# ---- A4/A5: interval indices, bit-exact ------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("kind,degree", [("linear", 0), ("constant", 0), ("bspline", 1), ("bspline", 3), ("bspline", 5)])
+@pytest.mark.parametrize("uniform", [False, True])
+def test_idx_eval_bit_exact(D, dtype, kind, degree, uniform):
+    rng = np.random.default_rng(7)
+    t = H.knots(rng, 37, dtype, uniform)
+    x = H.query(rng, t, 5000, dtype)
+    special = np.array([0.0, -0.0, np.nan, np.inf, -np.inf, np.finfo(dtype).max, -np.finfo(dtype).max], dtype=dtype)
+    x = np.concatenate([x, special, np.nextafter(t, dtype(np.inf)), np.nextafter(t, dtype(-np.inf))]).astype(dtype)
+    dim = H.make_dims(D, [kind], [t], [x], degrees=[degree])[0]
+    ref = O.get_idx(kind, t, x, degree=degree, dtype=dtype)
+    assert np.array_equal(dim.idx_eval, ref)
+
+
+def test_idx_eval_signed_zero_knots(D):
+    for t in ([-1.0, 0.0, 1.0], [-1.0, -0.0, 1.0]):
+        x = np.array([-0.0, 0.0, 1e-300, -1e-300])
+        for kind in ("linear", "constant"):
+            dim = H.make_dims(D, [kind], [np.array(t)], [x])[0]
+            assert np.array_equal(dim.idx_eval, O.get_idx(kind, t, x))
+
+
+def test_idx_eval_with_multiplicities(D):
+    t = np.array([0.0, 0.7, 1.1, 2.9, 4.0])
+    m = [3, 1, 2, 1, 3]
+    x = np.concatenate([t, np.linspace(-1, 5, 301)])
+    dim = D.BSplineInterpolationDimension(t, 2, t_eval=x, multiplicities=m)
+    assert np.array_equal(dim.idx_eval, O.get_idx("bspline", t, x, degree=2, multiplicities=m))
+    assert np.array_equal(dim.knots_all, O.expand_knots(t, 2, m))
+
+
+# ---- A7/A8: Cox–de Boor basis cache ------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("degree", [0, 1, 2, 3, 4, 5, 7])
+def test_basis_function_eval_cache(D, dtype, degree):
+    rng = np.random.default_rng(11)
+    t = H.knots(rng, 12, dtype)
+    x = H.query(rng, t, 400, dtype)
+    max_r = min(degree + 1, 3)
+    dim = D.BSplineInterpolationDimension(t, degree, t_eval=x, max_derivative_order_eval=max_r)
+    ref = O.basis(t, degree, x, max_derivative_order_eval=max_r, dtype=dtype)
+    got = dim.basis_function_eval
+    assert got.shape == ref.shape == (x.size, degree + 1, max_r + 1)
+    for r in range(max_r + 1):
+        H.assert_close(got[:, :, r], ref[:, :, r], dtype, factor=4.0)
+
+
+# ---- A9-A13: evaluators, unstructured and grid, all kinds ------------------------------------------
+def _case(rng, kinds, degrees, n_knots, out_dims, dtype, nurbs=False):
+    ts = [H.knots(rng, n, dtype, uniform=(i % 2 == 1)) for i, n in enumerate(n_knots)]
+    n_u = []
+    for k, p, t in zip(kinds, degrees, ts):
+        n_u.append(t.size + p - 1 if k == "bspline" else t.size)
+    u = rng.random(tuple(n_u) + tuple(out_dims)).astype(dtype)
+    w = (0.5 + rng.random(tuple(n_u))).astype(dtype) if nurbs else None
+    return ts, u, w
+
+
+CASES = [
+    # kinds, degrees, knots per dim, out dims, derivative orders to test
+    (("linear",), (0,), (9,), (), [(0,), (1,), (2,)]),
+    (("linear",) * 2, (0, 0), (8, 7), (2,), [(0, 0), (1, 0), (0, 1), (1, 1), (2, 0)]),
+    (("linear",) * 3, (0,) * 3, (6, 5, 7), (), [(0, 0, 0), (0, 1, 0)]),
+    (("linear",) * 5, (0,) * 5, (4, 3, 4, 3, 5), (4,), [(0,) * 5, (0, 0, 1, 0, 0)]),
+    (("constant",), (0,), (9,), (), [(0,), (1,)]),
+    (("constant",) * 2, (0, 0), (6, 7), (3,), [(0, 0), (1, 0)]),
+    (("bspline",), (3,), (9,), (), [(0,), (1,), (2,), (3,)]),
+    (("bspline",) * 2, (2, 3), (7, 6), (2,), [(0, 0), (1, 0), (0, 1), (1, 1), (2, 1)]),
+    (("bspline",) * 2, (5, 1), (7, 6), (), [(0, 0), (1, 1)]),
+    (("bspline",) * 3, (3, 3, 3), (6, 5, 7), (3,), [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)]),
+    (("bspline",) * 4, (2,) * 4, (5, 4, 5, 4), (), [(0,) * 4]),
+    (("bspline", "constant", "bspline"), (2, 0, 3), (6, 5, 6), (), [(0, 0, 0), (1, 0, 0)]),
+    (("linear", "bspline"), (0, 2), (6, 5), (2,), [(0, 0), (1, 1)]),
+    (("constant", "linear", "bspline"), (0, 0, 1), (4, 5, 6), (), [(0, 0, 0), (0, 1, 0)]),
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("flags", [0, GENERIC])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_unstructured_parity(D, dtype, flags, case):
+    kinds, degrees, n_knots, out_dims, orders_list = CASES[case]
+    rng = np.random.default_rng(100 + case)
+    ts, u, _ = _case(rng, kinds, degrees, n_knots, out_dims, dtype)
+    xs = H.zipped_queries(rng, ts, 3000, dtype)
+    for orders in orders_list:
+        kw = dict(degrees=degrees, derivative_orders=orders)
+        ref = H.oracle_eval(kinds, ts, u, xs, **kw)
+        if "constant" in kinds and any(o > 0 for o in orders) and out_dims:
+            out = np.full(ref.shape, 7.25, dtype=dtype, order="F")
+            ref = O.evaluate(kinds, ts, u, xs, out=out.copy(order="F"), **kw)
+            got, _ = H.gpu_eval(D, kinds, ts, u, xs, flags=flags, out=out, **kw)
+        else:
+            got, _ = H.gpu_eval(D, kinds, ts, u, xs, flags=flags, **kw)
+        H.assert_close(got, ref, dtype, factor=4.0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("flags", [0, GENERIC])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_grid_parity(D, dtype, flags, case):
+    kinds, degrees, n_knots, out_dims, orders_list = CASES[case]
+    rng = np.random.default_rng(200 + case)
+    ts, u, _ = _case(rng, kinds, degrees, n_knots, out_dims, dtype)
+    n_per = {1: 600, 2: 45, 3: 14, 4: 7, 5: 5}[len(kinds)]
+    xs = [np.sort(H.query(rng, t, n_per, dtype)) if i % 2 == 0 else H.query(rng, t, n_per, dtype) for i, t in enumerate(ts)]
+    for orders in orders_list:
+        kw = dict(degrees=degrees, derivative_orders=orders, grid=True)
+        ref = H.oracle_eval(kinds, ts, u, xs, **kw)
+        if "constant" in kinds and any(o > 0 for o in orders) and out_dims:
+            out = np.full(ref.shape, 7.25, dtype=dtype, order="F")
+            ref = O.evaluate(kinds, ts, u, xs, out=out.copy(order="F"), **kw)
+            got, _ = H.gpu_eval(D, kinds, ts, u, xs, flags=flags, out=out, **kw)
+        else:
+            got, _ = H.gpu_eval(D, kinds, ts, u, xs, flags=flags, **kw)
+        H.assert_close(got, ref, dtype, factor=4.0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("flags", [0, GENERIC])
+@pytest.mark.parametrize("n_in,degree,out_dims", [(1, 2, (2,)), (2, 3, ()), (2, 1, (3,)), (3, 2, ()), (4, 2, ())])
+def test_nurbs_parity(D, dtype, flags, n_in, degree, out_dims):
+    rng = np.random.default_rng(300 + n_in)
+    kinds, degrees = ("bspline",) * n_in, (degree,) * n_in
+    ts, u, w = _case(rng, kinds, degrees, (6, 5, 6, 5)[:n_in], out_dims, dtype, nurbs=True)
+    xs = H.zipped_queries(rng, ts, 2000, dtype)
+    ref = H.oracle_eval(kinds, ts, u, xs, degrees=degrees, weights=w)
+    got, _ = H.gpu_eval(D, kinds, ts, u, xs, degrees=degrees, weights=w, flags=flags)
+    H.assert_close(got, ref, dtype, factor=8.0)
+    n_per = {1: 300, 2: 40, 3: 12, 4: 6}[n_in]
+    xg = [np.sort(H.query(rng, t, n_per, dtype)) for t in ts]
+    ref = H.oracle_eval(kinds, ts, u, xg, degrees=degrees, weights=w, grid=True)
+    got, _ = H.gpu_eval(D, kinds, ts, u, xg, degrees=degrees, weights=w, grid=True, flags=flags)
+    H.assert_close(got, ref, dtype, factor=8.0)
+
+
+def test_cached_idx_path_matches(D):
+    rng = np.random.default_rng(5)
+    kinds, degrees = ("bspline",) * 2, (3, 2)
+    ts, u, _ = _case(rng, kinds, degrees, (7, 6), (2,), np.float64)
+    xs = H.zipped_queries(rng, ts, 2000, np.float64)
+    a, _ = H.gpu_eval(D, kinds, ts, u, xs, degrees=degrees, flags=0)
+    b, _ = H.gpu_eval(D, kinds, ts, u, xs, degrees=degrees, flags=CACHED_IDX)
+    c, _ = H.gpu_eval(D, kinds, ts, u, xs, degrees=degrees, flags=CACHED_IDX | GENERIC)
+    assert np.array_equal(a, b)
+    H.assert_close(c, a, np.float64)
+
+
+# ---- the reference's known-answer tests, on the GPU --------------------------------------------
+T1 = np.array([-3.14, 1.0, 3.0, 7.6, 12.8])
+T2 = np.array([-2.71, 1.41, 12.76, 50.2, 120.0])
+
+
+def _mid(t):
+    return t[:-1] + np.diff(t) / 2
+
+
+@pytest.mark.parametrize("case", ["linear", "bspline", "nurbs"])
+def test_kat_globally_constant(D, case):   # test/test_interpolations.jl:5-50, :68, :86-90, :108-114
+    rng = np.random.default_rng(10)
+    if case == "linear":
+        kinds, degs, u, w, derivs = ["linear"] * 2, None, np.full((5, 5), 2.0), None, True
+    elif case == "bspline":
+        kinds, degs, u, w, derivs = ["bspline"] * 2, [2, 3], np.full((6, 7), 2.0), None, True
+    else:
+        kinds, degs, u, w, derivs = ["bspline"] * 2, [3, 1], np.full((7, 5), 2.0), rng.random((7, 5)), False
+    for te in ((T1, T2), (_mid(T1), _mid(T2))):
+        val, _ = H.gpu_eval(D, kinds, [T1, T2], u, te, degrees=degs, weights=w, grid=True)
+        np.testing.assert_allclose(val, 2.0, atol=1e-10, rtol=0)
+        if derivs:
+            for orders in ((1, 0), (0, 1)):
+                d, _ = H.gpu_eval(D, kinds, [T1, T2], u, te, degrees=degs, derivative_orders=orders, grid=True)
+                np.testing.assert_allclose(d, 0.0, atol=1e-10, rtol=0)
+
+
+def test_kat_linear_plane_single_point(D):   # test/test_interpolations.jl:52-82
+    rng = np.random.default_rng(1)
+    t1, t2 = np.cumsum(rng.random(10)), np.cumsum(rng.random(10))
+    f = lambda a, b: 3.0 + 2.3 * a - 4.7 * b
+    itp = D.NDInterpolation(f(t1[:, None], t2[None, :]), (D.LinearInterpolationDimension(t1), D.LinearInterpolationDimension(t2)))
+    for ts in ((t1, t2), (_mid(t1), _mid(t2))):
+        for a, b in itertools.product(*ts):
+            assert itp(a, b) == pytest.approx(f(a, b), rel=1e-12, abs=1e-12)
+    itp.close()
+
+
+def test_kat_bspline_quadratic_net(D):   # test/test_interpolations.jl:92-102
+    u = np.zeros((3, 3, 3))
+    u[1, 1, 1] = -3
+    for I in itertools.product((0, 2), repeat=3):
+        u[I] = 3
+    t = np.array([-1.0, 1.0])
+    dim = D.BSplineInterpolationDimension(t, 2)
+    itp = D.NDInterpolation(u, (dim, dim, dim))
+    for ts in ((t,) * 3, (_mid(t),) * 3):
+        for x in itertools.product(*ts):
+            assert itp(*x) == pytest.approx(sum(v * v for v in x), abs=1e-13)
+    itp.close()
+
+
+@pytest.mark.parametrize("grid", [True, False])
+def test_kat_nurbs_unit_circle(D, grid):   # test/test_interpolations.jl:116-149, test/test_interface.jl:270-292
+    t = np.arange(5) * (np.pi / 2)
+    t_eval = np.linspace(0, 2 * np.pi, 100)
+    u = np.array([[1, 0], [1, 1], [0, 1], [-1, 1], [-1, 0], [-1, -1], [0, -1], [1, -1], [1, 0]], dtype=np.float64)
+    w = np.ones(9)
+    w[1::2] /= np.sqrt(2)
+    dim = D.BSplineInterpolationDimension(t, 2, multiplicities=[3, 2, 2, 2, 3], t_eval=t_eval)
+    itp = D.NDInterpolation(u, dim, cache=D.NURBSWeights(w))
+    out = (D.eval_grid if grid else D.eval_unstructured)(itp)
+    assert out.shape == (100, 2)
+    np.testing.assert_allclose(out[:, 0] ** 2 + out[:, 1] ** 2, 1.0, atol=1e-13, rtol=0)
+    assert len({tuple(r) for r in out[1:]}) == 99
+    itp.close()
+
+
+def test_kat_1d_tables(D):   # test/test_datainterpolations_comparison.jl:6-75
+    t = np.array([0.0, 0.2, 0.5, 0.7, 0.9, 1.1])
+    u = np.array([1.5, -5.3, 0.5, 3.3, 3.6, 1.0])
+    xi = np.concatenate([np.linspace(t[i], t[i + 1], 25)[1:24] for i in range(5)])
+    x = np.concatenate([xi, t])
+    lin = D.NDInterpolation(u, D.LinearInterpolationDimension(t, t_eval=x))
+    np.testing.assert_allclose(D.eval_unstructured(lin), np.interp(x, t, u), rtol=1e-12, atol=1e-13)
+    slopes = np.diff(u) / np.diff(t)
+    d = D.eval_unstructured(lin, derivative_orders=(1,))
+    np.testing.assert_allclose(d[: xi.size], slopes[np.searchsorted(t, xi, side="left") - 1], rtol=1e-12)
+    np.testing.assert_allclose(d[xi.size:], slopes[[0, 0, 1, 2, 3, 4]], rtol=1e-12)
+    con = D.NDInterpolation(u, D.ConstantInterpolationDimension(t, t_eval=x))
+    v = D.eval_unstructured(con)
+    assert np.array_equal(v[: xi.size], u[np.searchsorted(t, xi, side="right") - 1])
+    assert np.array_equal(v[xi.size:], u)
+    dc = D.eval_unstructured(con, derivative_orders=(1,))
+    assert np.all(dc[: xi.size] == 0) and np.all(np.isnan(dc[xi.size:]))
+    lin.close(); con.close()
+
+
+def test_golden_scipy_vectors_on_gpu(D, golden):
+    for p in (1, 2, 3, 4, 5):
+        t, u, x = (golden[f"bs1d_p{p}_{k}"] for k in "tux")
+        for r in range(4):
+            got, _ = H.gpu_eval(D, ["bspline"], [t], u, [x], degrees=[p], derivative_orders=[r])
+            H.assert_close(got, golden[f"bs1d_p{p}_r{r}"], np.float64, factor=20.0)
+    ta, tb, u, xa, xb = (golden[f"bs2d_{k}"] for k in ("ta", "tb", "u", "xa", "xb"))
+    for ra, rb in ((0, 0), (1, 0), (0, 1), (1, 1), (2, 1)):
+        kw = dict(degrees=[2, 3], derivative_orders=[ra, rb])
+        got, _ = H.gpu_eval(D, ["bspline"] * 2, [ta, tb], u, [xa, xb], grid=True, **kw)
+        H.assert_close(got, golden[f"bs2d_grid_r{ra}{rb}"], np.float64, factor=20.0)
+        got, _ = H.gpu_eval(D, ["bspline"] * 2, [ta, tb], u, [xa, xb], **kw)
+        H.assert_close(got, golden[f"bs2d_unst_r{ra}{rb}"], np.float64, factor=20.0)
+    for nd in (2, 3, 5):
+        ts = [golden[f"lin{nd}d_t{d}"] for d in range(nd)]
+        xs = [golden[f"lin{nd}d_x{d}"] for d in range(nd)]
+        got, _ = H.gpu_eval(D, ["linear"] * nd, ts, golden[f"lin{nd}d_u"], xs)
+        H.assert_close(got, golden[f"lin{nd}d_val"], np.float64, factor=20.0)
+
+
+# ---- interface behaviour ---------------------------------------------------------------------------
+def test_float32_in_float32_out_and_promotion(D):   # test/test_interface.jl:161-215
+    t = np.array([1, 2, 3, 4], dtype=np.float32)
+    u = np.random.default_rng(0).random((4, 4)).astype(np.float32)
+    te = np.array([1.5, 2.5], dtype=np.float32)
+    dims = (D.LinearInterpolationDimension(t, t_eval=te),) * 2
+    itp = D.NDInterpolation(u, dims)
+    out = D.eval_grid(itp)
+    assert out.dtype == np.float32 and out.shape == (2, 2)
+    assert itp.dtype == np.float32
+    itp64 = D.NDInterpolation(u.astype(np.float64), (D.LinearInterpolationDimension(t),) * 2)
+    assert itp64.dtype == np.float64
+    assert isinstance(float(itp64(1.5, 2.5)), float)
+    itp.close(); itp64.close()
+
+
+def test_validation_errors(D):
+    t = np.array([0.0, 1.0, 2.0])
+    with pytest.raises(AssertionError):
+        D.LinearInterpolationDimension([0.0, 0.0, 1.0])
+    with pytest.raises(AssertionError):   # validate_size_u
+        D.NDInterpolation(np.zeros((4, 3)), (D.LinearInterpolationDimension(t),) * 2)
+    with pytest.raises(AssertionError):   # multiplicities out of range
+        D.BSplineInterpolationDimension(t, 2, multiplicities=[3, 4, 3])
+    bs = D.BSplineInterpolationDimension(t, 2, t_eval=[0.5, 1.5])
+    itp = D.NDInterpolation(np.zeros(4), bs)
+    with pytest.raises(AssertionError):   # derivative order > max_derivative_order_eval
+        D.eval_unstructured(itp, derivative_orders=(1,))
+    with pytest.raises(AssertionError):   # negative order
+        D.eval_unstructured(itp, derivative_orders=(-1,))
+    itp.close()
+    nur = D.NDInterpolation(np.zeros(4), D.BSplineInterpolationDimension(t, 2, t_eval=[0.5], max_derivative_order_eval=1),
+                            cache=D.NURBSWeights(np.ones(4)))
+    with pytest.raises(AssertionError):   # NURBS derivatives unsupported
+        D.eval_unstructured(nur, derivative_orders=(1,))
+    nur.close()
+    with pytest.raises(AssertionError):   # weights size
+        D.NDInterpolation(np.zeros(4), D.BSplineInterpolationDimension(t, 2), cache=D.NURBSWeights(np.ones(5)))
+    itp2 = D.NDInterpolation(np.zeros((3, 3)), (D.LinearInterpolationDimension(t, t_eval=[0.1, 0.2]),
+                                                D.LinearInterpolationDimension(t, t_eval=[0.1])))
+    with pytest.raises(AssertionError):   # unequal t_eval lengths for unstructured
+        D.eval_unstructured(itp2)
+    assert D.eval_grid(itp2).shape == (2, 1)
+    itp2.close()
+
+
+def test_single_point_in_place_and_eval_points(D):   # src/DataInterpolationsND.jl:85-94
+    rng = np.random.default_rng(2)
+    t1, t2 = H.knots(rng, 6), H.knots(rng, 7)
+    u = rng.random((6, 7, 3))
+    itp = D.NDInterpolation(u, (D.LinearInterpolationDimension(t1), D.LinearInterpolationDimension(t2)))
+    out = np.zeros(3)
+    itp(2.0, 3.0, out=out)
+    ref = O.point(["linear"] * 2, [t1, t2], u, (2.0, 3.0))
+    np.testing.assert_allclose(out, ref, rtol=1e-13)
+    with pytest.raises(AssertionError):
+        itp(2.0, 3.0, out=np.zeros(4))
+    xs = [rng.uniform(t1[0], t1[-1], 100), rng.uniform(t2[0], t2[-1], 100)]
+    got = itp.eval_points(xs, derivative_orders=(1, 0))
+    H.assert_close(got, O.evaluate(["linear"] * 2, [t1, t2], u, xs, derivative_orders=(1, 0)), np.float64)
+    itp.close()
+
+
+def test_empty_and_single_point_batches(D):
+    t = np.array([0.0, 1.0, 2.0])
+    itp = D.NDInterpolation(np.array([1.0, 2.0, 4.0]), D.LinearInterpolationDimension(t))
+    assert D.eval_unstructured(itp).shape == (0,)          # t_eval defaults to no points
+    assert D.eval_grid(itp).shape == (0,)
+    itp.close()
+    itp = D.NDInterpolation(np.array([1.0, 2.0, 4.0]), D.LinearInterpolationDimension(t, t_eval=[1.5]))
+    assert D.eval_unstructured(itp).tolist() == [3.0]
+    itp.close()
+
+
+def test_device_tensors_zero_copy_and_new_u(D):
+    import torch
+    rng = np.random.default_rng(4)
+    ts = [H.knots(rng, 9, np.float32) for _ in range(3)]
+    xs = [np.sort(rng.uniform(t[0], t[-1], 17)).astype(np.float32) for t in ts]
+    dims = tuple(D.LinearInterpolationDimension(t, t_eval=torch.from_numpy(x).cuda()) for t, x in zip(ts, xs))
+    u0 = rng.random((9, 9, 9)).astype(np.float32)
+    ud = D.f_empty(u0.shape, np.float32, "cuda")
+    ud.copy_(torch.from_numpy(u0))
+    itp = D.NDInterpolation(ud, dims)
+    out = D.eval_grid(itp)
+    assert out.is_cuda
+    H.assert_close(out.cpu().numpy(), O.evaluate(["linear"] * 3, ts, u0, xs, grid=True), np.float32)
+    # "repeated with new u": same caches, new data written into the borrowed device buffer
+    u1 = rng.random((9, 9, 9)).astype(np.float32)
+    ud.copy_(torch.from_numpy(u1))
+    out2 = D.f_empty(out.shape, np.float32, "cuda")
+    D.eval_grid_(out2, itp)
+    H.assert_close(out2.cpu().numpy(), O.evaluate(["linear"] * 3, ts, u1, xs, grid=True), np.float32)
+    itp.close()
