@@ -204,7 +204,9 @@ __device__ __forceinline__ void dim_stencil(const DimParams<T>& D, T x, int orde
         idx1 = idx;
         i0 = (x >= D.knots[n - 1]) ? n - 1 : idx - 1;                       // :57-59
         w[0] = T(1);
-        if (order > 0) on_knot = count_lt(D.keys, n, kx) < cnt;             // :50 !isempty(searchsorted(t, x))
+        // :50 !isempty(searchsorted(t, x)); only consulted when some Constant dimension has a
+        // derivative order > 0 (the reference then tests every dimension, not only that one)
+        on_knot = count_lt(D.keys, n, kx) < cnt;
     } else {
         const int p = D.degree;
         const int idx = cached_idx ? cached_idx : clampi(count_le(D.keys, n, kx), p + 1, n - p - 1);

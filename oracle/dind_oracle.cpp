@@ -290,8 +290,8 @@ PointStatus interpolate_bspline(T* out, int64_t out_stride, const Interp<T>& A, 
 //   Constant -> 1 point (index rule of interpolation_methods.jl:57-59), weight 1;
 //   Linear   -> 2 points, weights (t2-x, x-t1)/(t2-t1) or (-1, 1)/(t2-t1) (order 1), 0 for order > 1;
 //   BSpline  -> degree+1 points, Cox–de Boor values.
-// A Constant dimension with derivative order > 0 follows the Constant rule (NaN on a
-// knot, else zero / untouched).  NURBS weights multiply in as in :124-138.
+// A Constant dimension with derivative order > 0 follows the Constant rule (NaN when any
+// Constant dimension sits on a knot, else zero / untouched).  NURBS weights multiply in as in :124-138.
 // ---------------------------------------------------------------------------
 template <class T>
 PointStatus interpolate_mixed(T* out, int64_t out_stride, const Interp<T>& A, const T* t,
@@ -300,8 +300,9 @@ PointStatus interpolate_mixed(T* out, int64_t out_stride, const Interp<T>& A, co
     bool const_deriv = false, on_knot = false;
     for (int i = 0; i < N; ++i) {
         const Dim<T>& d = A.dims[i];
-        if (d.kind == CONSTANT && orders[i] > 0) {
-            const_deriv = true;
+        if (d.kind == CONSTANT) {
+            if (orders[i] > 0) const_deriv = true;
+            // like :50 — every Constant dimension is tested, not only the differentiated one
             if (searchsortedfirst(d.t, d.n_t, t[i]) <= searchsortedlast(d.t, d.n_t, t[i])) on_knot = true;
         }
     }

@@ -83,8 +83,8 @@ def query(rng, t, n, dtype=np.float64, with_knots=True, outside=True):
     return x.astype(dtype)
 
 
-def zipped_queries(rng, ts, n, dtype):
+def zipped_queries(rng, ts, n, dtype, outside=True):
     """Equal-length per-dimension query vectors (each including knots / outside points)."""
-    xs = [query(rng, t, n, dtype) for t in ts]
+    xs = [query(rng, t, n, dtype, outside=outside) for t in ts]
     m = min(x.size for x in xs)
     return [x[:m] for x in xs]

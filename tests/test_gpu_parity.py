@@ -151,12 +151,14 @@ def test_nurbs_parity(D, dtype, flags, n_in, degree, out_dims):
     rng = np.random.default_rng(300 + n_in)
     kinds, degrees = ("bspline",) * n_in, (degree,) * n_in
     ts, u, w = _case(rng, kinds, degrees, (6, 5, 6, 5)[:n_in], out_dims, dtype, nurbs=True)
-    xs = H.zipped_queries(rng, ts, 2000, dtype)
+    # inside the knot span only: a rational function extrapolated outside it has poles (the
+    # denominator sum(w*B) changes sign), where comparing two roundings is meaningless
+    xs = H.zipped_queries(rng, ts, 2000, dtype, outside=False)
     ref = H.oracle_eval(kinds, ts, u, xs, degrees=degrees, weights=w)
     got, _ = H.gpu_eval(D, kinds, ts, u, xs, degrees=degrees, weights=w, flags=flags)
     H.assert_close(got, ref, dtype, factor=8.0)
     n_per = {1: 300, 2: 40, 3: 12, 4: 6}[n_in]
-    xg = [np.sort(H.query(rng, t, n_per, dtype)) for t in ts]
+    xg = [np.sort(H.query(rng, t, n_per, dtype, outside=False)) for t in ts]
     ref = H.oracle_eval(kinds, ts, u, xg, degrees=degrees, weights=w, grid=True)
     got, _ = H.gpu_eval(D, kinds, ts, u, xg, degrees=degrees, weights=w, grid=True, flags=flags)
     H.assert_close(got, ref, dtype, factor=8.0)
