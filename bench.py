@@ -1,0 +1,447 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 evaluation engine (BASELINE.json metric:
+Gpoints/s for eval_unstructured / eval_grid!, fraction of the HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c5] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+  c2 (default, BASELINE configs[1]): 3-D trilinear scalar field u = 256^3 Float32, eval_grid!
+      onto a 512^3 t_eval grid with cached per-axis indices/weights, a fresh `u` each step.
+  c1 / c3 / c5: the unstructured configs; c3/c5 at a reduced point count unless --full.
+Multi-GPU (torchrun, one rank per GPU): grids are sharded by slab along the last axis, point
+lists by contiguous index range, u and knots replicated, no data-path collective; the global
+problem grows with N (weak scaling): c2 at N GPUs is a 512 x 512 x (512*N) grid.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference
+(oracle/, OpenMP over all host cores: the reference itself is Julia and cannot run here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Gpoints/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# ---- workloads -------------------------------------------------------------------------------------
+def knots_1d(rng, n, dtype):
+    return np.cumsum(0.5 + rng.random(n)).astype(dtype)   # docs/src/usage.md:11-12 style, non-uniform
+
+
+class Workload:
+    name = ""
+    dtype = np.float32
+    kinds = ()
+    degrees = None
+
+    def host_inputs(self, rank, world):
+        raise NotImplementedError
+
+
+class C2(Workload):
+    """3-D trilinear, u 256^3 F32 -> 512^3 grid (per GPU), slab-sharded along axis 3."""
+    name = "c2: 3-D trilinear u=256^3 Float32, eval_grid! onto 512^3 (cached idx, new u each step)"
+    key = "c2"
+    dtype = np.float32
+    dtype_name = "f32"
+    grid = True
+    n_u = (256, 256, 256)
+    n_grid = (512, 512, 512)   # per GPU
+    n_u_buffers = 4            # u rotates over 4 x 67 MB buffers so it is never L2-resident at step start
+
+    def __init__(self, scale=1.0):
+        if scale != 1.0:
+            self.n_grid = tuple(max(8, int(g * scale)) for g in self.n_grid)
+            self.n_u = tuple(max(8, int(g * scale)) for g in self.n_u)
+
+    def points_per_step(self):
+        return int(np.prod(self.n_grid))
+
+    def alg_bytes(self):
+        # out write (4 B/pt) + one read of u per launch
+        return self.points_per_step() * 4 + int(np.prod(self.n_u)) * 4
+
+    def build(self, rank, world):
+        rng = np.random.default_rng(1234)
+        self.ts = [knots_1d(rng, n, self.dtype) for n in self.n_u]
+        # global grid: axis 3 has n_grid[2] * world points, rank r owns slab r
+        self.t_evals = []
+        for d, (t, g) in enumerate(zip(self.ts, self.n_grid)):
+            if d == 2:
+                full = np.linspace(t[0], t[-1], g * world).astype(self.dtype)
+                self.t_evals.append(full[rank * g:(rank + 1) * g])
+            else:
+                self.t_evals.append(np.linspace(t[0], t[-1], g).astype(self.dtype))
+        self.u_rng = np.random.default_rng(99 + rank)
+
+
+class Unstructured(Workload):
+    grid = False
+
+    def points_per_step(self):
+        return self.n_points
+
+    def build(self, rank, world):
+        rng = np.random.default_rng(1234)
+        self.ts = [knots_1d(rng, n, self.dtype) for n in self.n_knots]
+        self.rank, self.world = rank, world
+
+
+class C1(Unstructured):
+    name = "c1: 2-D linear u=(64,64,2) Float64, eval_unstructured at 1e6 zipped points"
+    key, dtype, dtype_name = "c1", np.float64, "f64"
+    kinds, degrees, n_knots, n_u, n_points = ("linear",) * 2, (0, 0), (64, 64), (64, 64, 2), 10 ** 6
+
+    def alg_bytes(self):
+        return self.n_points * 32 + 64 * 64 * 2 * 8
+
+
+class C3(Unstructured):
+    name = "c3: 3-D cubic BSpline u=(128,128,128,3) Float64, eval_unstructured"
+    key, dtype, dtype_name = "c3", np.float64, "f64"
+    kinds, degrees, n_knots, n_u = ("bspline",) * 3, (3, 3, 3), (126,) * 3, (128, 128, 128, 3)
+
+    def __init__(self, n_points):
+        self.n_points = n_points
+
+    def alg_bytes(self):
+        return self.n_points * 48 + 128 ** 3 * 3 * 8
+
+
+class C5(Unstructured):
+    name = "c5: 5-D linear lookup table u=(32^5,4) Float32, eval_unstructured"
+    key, dtype, dtype_name = "c5", np.float32, "f32"
+    kinds, degrees, n_knots, n_u = ("linear",) * 5, (0,) * 5, (32,) * 5, (32,) * 5 + (4,)
+
+    def __init__(self, n_points):
+        self.n_points = n_points
+
+    def alg_bytes(self):
+        return self.n_points * 36 + 32 ** 5 * 4 * 4
+
+
+# ---- clocks sampling -----------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, device):
+        self.samples, self.reasons, self.stop = [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        while not self.stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        if self.nv:
+            self.th.join(timeout=1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ---- GPU arm ------------------------------------------------------------------------------------------
+def run_gpu(args, wl, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import dind_b200 as D
+
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    wl.build(rank, world)
+    stream = torch.cuda.current_stream()
+    tdt = torch.float32 if wl.dtype == np.float32 else torch.float64
+
+    def to_dev(a):
+        t = D.f_empty(a.shape, wl.dtype, dev)
+        t.copy_(torch.from_numpy(np.ascontiguousarray(a)).to(dev))
+        return t
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1000 + rank)
+    if wl.grid:
+        dims = tuple(D.LinearInterpolationDimension(t, t_eval=to_dev(x)) for t, x in zip(wl.ts, wl.t_evals))
+        u_bufs = []
+        for _ in range(wl.n_u_buffers):
+            ub = D.f_empty(wl.n_u, wl.dtype, dev)
+            ub.copy_(torch.rand(wl.n_u[::-1], generator=gen, device=dev, dtype=tdt).permute(2, 1, 0))
+            u_bufs.append(ub)
+        itp = D.NDInterpolation(u_bufs[0], dims, device=local_rank, stream=stream.cuda_stream)
+        out = D.f_empty(wl.n_grid, wl.dtype, dev)
+
+        def step(i):
+            itp.set_u(u_bufs[i % len(u_bufs)])          # "repeated with new u": borrowed device pointer, no copy
+            D.eval_grid_(out, itp, flags=1)             # DIND_FLAG_ASYNC: stay on the stream, timed with CUDA events
+    else:
+        lo, hi = D.shard_range(wl.n_points * world, rank, world)   # weak scaling: n_points per rank
+        n = hi - lo
+        mk = {"linear": lambda t, p, x: D.LinearInterpolationDimension(t, t_eval=x),
+              "bspline": lambda t, p, x: D.BSplineInterpolationDimension(t, p, t_eval=x, max_derivative_order_eval=1)}
+        xs = []
+        for t in wl.ts:
+            x = torch.rand(n, generator=gen, device=dev, dtype=tdt) * float(t[-1] - t[0]) + float(t[0])
+            xs.append(x)
+        dims = tuple(mk[k](t, p, x) for k, t, p, x in zip(wl.kinds, wl.ts, wl.degrees, xs))
+        shape = tuple(wl.n_u)
+        ud = D.f_empty(shape, wl.dtype, dev)
+        ud.copy_(torch.rand(shape[::-1], generator=gen, device=dev, dtype=tdt).permute(*reversed(range(len(shape)))))
+        itp = D.NDInterpolation(ud, dims, device=local_rank, stream=stream.cuda_stream)
+        out = D.f_empty((n,) + shape[len(wl.kinds):], wl.dtype, dev)
+
+        def step(i):
+            D.eval_unstructured_(out, itp, flags=1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    l0 = itp.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        for i in range(args.steps):
+            step(args.warmup + i)
+        ev1.record(stream)
+        barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = itp.launch_count - l0
+    kernel = itp.last_kernel
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    e2e_ms, h2d, d2h = None, 0, 0
+    if wl.grid:
+        u_host = [torch.rand(wl.n_u[::-1], dtype=tdt).pin_memory() for _ in range(2)]
+        out_host = torch.empty(wl.n_grid[::-1], dtype=tdt).pin_memory()
+        u_np = [t.numpy().transpose(2, 1, 0) for t in u_host]          # column-major views of the pinned buffers
+        out_np = out_host.numpy().transpose(2, 1, 0)
+        itp_h = D.NDInterpolation(u_np[0], tuple(D.LinearInterpolationDimension(t, t_eval=x) for t, x in zip(wl.ts, wl.t_evals)),
+                                  device=local_rank, stream=stream.cuda_stream)
+        n_e2e = max(2, min(args.steps, 5))
+        for i in range(2):
+            itp_h.set_u(u_np[i % 2]); D.eval_grid_(out_np, itp_h)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            itp_h.set_u(u_np[i % 2])         # H2D of this step's u
+            D.eval_grid_(out_np, itp_h)      # kernel + D2H of the result, synchronous like the reference
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+        h2d, d2h = int(np.prod(wl.n_u)) * 4, wl.points_per_step() * 4
+        itp_h.close()
+    else:
+        n = out.shape[0]
+        n_h = min(n, 20_000_000)
+        xs_h = [x[:n_h].cpu().pin_memory() for x in xs]
+        out_h = torch.empty((int(np.prod(out.shape[1:])) if out.ndim > 1 else 1, n_h), dtype=tdt).pin_memory()
+        out_np = out_h.numpy().T if out.ndim > 1 else out_h.numpy().reshape(-1)
+        out_np = out_np.reshape((n_h,) + tuple(out.shape[1:]), order="F") if out.ndim > 1 else out_np
+        pts = [x.numpy() for x in xs_h]
+        for _ in range(2):
+            itp.eval_points(pts, out=out_np)
+        barrier()
+        n_e2e = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            itp.eval_points(pts, out=out_np)   # H2D of the points + kernel + D2H of the result
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e * (n / n_h)   # scaled to the full per-step point count
+        esz = np.dtype(wl.dtype).itemsize
+        h2d, d2h = n * esz * len(pts), int(np.prod(out.shape)) * esz
+
+    # max over ranks
+    vals = torch.tensor([ms_total, e2e_ms or 0.0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(vals[0]), float(vals[1])
+    ms_per_step = ms_total / args.steps
+    pts_step_all = wl.points_per_step() * world
+    value = pts_step_all / (ms_per_step * 1e-3) / 1e9
+    peaks, peak_src = measured_peaks()
+    achieved = wl.alg_bytes() / (ms_per_step * 1e-3) / 1e9     # per GPU: one launch per step per rank
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": "Gpoints/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": wl.dtype_name, "data": "synthetic",
+        "config": {"workload": wl.name, "points_per_step_per_gpu": wl.points_per_step(),
+                   "sharding": ("slab along the last grid axis" if wl.grid else "contiguous index range") + ", u/knots replicated, no collective",
+                   "l2": "working set exceeds L2 (126 MB): output streamed, u rotates over 4 buffers" if wl.grid else "t_eval + out exceed L2",
+                   "kernel": kernel},
+        "e2e": {"value": round(pts_step_all / (e2e_ms * 1e-3) / 1e9, 4), "unit": "Gpoints/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "host (pinned) buffers through the public API; synchronous call incl. H2D + kernel + D2H"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": wl.alg_bytes()},
+        "clocks": clocks.summary(),
+    }
+    itp.close()
+    return line
+
+
+# ---- CPU arm (oracle port of the reference) -----------------------------------------------------------
+def cpu_sample(wl, seconds_target=12.0, nthreads=0):
+    """Times the CPU restatement of the reference on a bounded sample of the workload."""
+    from oracle import oracle as O
+    wl.build(0, 1)
+    rng = np.random.default_rng(5)
+    nthreads = nthreads or O.max_threads()
+    if wl.grid:
+        u = rng.random(wl.n_u, dtype=np.float32).astype(wl.dtype)
+        u = np.asfortranarray(u)
+        k = 2
+        sample = None
+        while True:
+            te = [wl.t_evals[0], wl.t_evals[1], wl.t_evals[2][:k]]
+            t0 = time.perf_counter()
+            O.evaluate(["linear"] * 3, wl.ts, u, te, grid=True, nthreads=nthreads)
+            dt = time.perf_counter() - t0
+            pts = int(np.prod([len(x) for x in te]))
+            sample = (pts, dt, f"{len(te[0])}x{len(te[1])}x{k} slab of the {wl.n_grid} grid, full u")
+            if dt > seconds_target / 3 or k >= len(wl.t_evals[2]):
+                break
+            k = min(len(wl.t_evals[2]), max(k * 2, int(k * seconds_target / 2 / max(dt, 1e-3))))
+        return sample[0] / sample[1] / 1e9, nthreads, sample[2]
+    shape = tuple(wl.n_u)
+    u = np.asfortranarray(rng.random(shape).astype(wl.dtype))
+    n = 200_000
+    while True:
+        xs = [rng.uniform(t[0], t[-1], n).astype(wl.dtype) for t in wl.ts]
+        t0 = time.perf_counter()
+        O.evaluate(list(wl.kinds), wl.ts, u, xs, degrees=list(wl.degrees), nthreads=nthreads)
+        dt = time.perf_counter() - t0
+        if dt > seconds_target / 3 or n >= wl.n_points:
+            return n / dt / 1e9, nthreads, f"{n} of {wl.n_points} points, full u"
+        n = min(wl.n_points, max(n * 2, int(n * seconds_target / 2 / max(dt, 1e-3))))
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return None
+    from oracle import oracle as O
+    nthreads = O.max_threads()
+    vals = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, _, sample = cpu_sample(wl, seconds_target=max(3.0, 60.0 / (args.warmup + args.steps)), nthreads=nthreads)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    return {
+        "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": "Gpoints/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": wl.dtype_name, "data": "synthetic",
+        "config": {"workload": wl.name, "note": "CPU restatement of the reference (oracle/, C++/OpenMP), not Julia: Julia is not in this image"},
+        "cpu_baseline": {"value": round(value, 5), "unit": "Gpoints/s", "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 5), "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def make_workload(args):
+    if args.workload == "c2":
+        return C2(args.scale)
+    if args.workload == "c1":
+        return C1()
+    if args.workload == "c3":
+        return C3(100_000_000 if args.full else 20_000_000)
+    if args.workload == "c5":
+        return C5(4_000_000_000 if args.full else 100_000_000)
+    raise SystemExit(f"unknown workload {args.workload}")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--impl", default="dind")
+    ap.add_argument("--full", action="store_true", help="full-size point counts for c3 / c5")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink c2 (debugging only; not a bench value)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    wl = make_workload(args)
+
+    if args.impl == "reference":
+        line = run_reference(args, wl, rank, world)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    line = run_gpu(args, wl, rank, world, local_rank)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_sample(make_workload(args))
+            line["cpu_baseline"] = {"value": round(v, 5), "unit": "Gpoints/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
