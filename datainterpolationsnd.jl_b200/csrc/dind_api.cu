@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -60,7 +61,8 @@ struct DevBuf {
 
 struct AxisTable {
     int order = -1;
-    DevBuf i0, w, flag;
+    DevBuf i0, w, flag, spans;
+    int span2 = -1, span4 = -1;   // see DimParams::group_span2/4
 };
 
 struct DimState {
@@ -87,7 +89,7 @@ struct DimState {
     }
     void release() {
         d_knots.release(); d_keys.release(); d_recip.release(); teval_owned.release();
-        d_idx.release(); table.i0.release(); table.w.release(); table.flag.release();
+        d_idx.release(); table.i0.release(); table.w.release(); table.flag.release(); table.spans.release();
     }
 };
 
@@ -187,6 +189,8 @@ DimParams<T> make_dim_params(const dind_interp_s* h, const DimState& D, int dim,
     P.width = D.width;
     P.n_u = (int32_t)D.n_u;
     P.order = order;
+    P.group_span2 = D.table.order >= 0 ? D.table.span2 : -1;
+    P.group_span4 = D.table.order >= 0 ? D.table.span4 : -1;
     return P;
 }
 
@@ -224,6 +228,17 @@ int ensure_table(dind_interp_s* h, int dim, int order) {
     DimParams<T> P = make_dim_params<T>(h, D, dim, order);
     CUDA_TRY(launch_axis_table<T>(P, order, (int32_t*)D.table.i0.p, (T*)D.table.w.p, (uint8_t*)D.table.flag.p, h->stream));
     h->launches += D.n_eval ? 1 : 0;
+    // how far the first stencil node moves inside aligned groups of 2 / 4 grid coordinates
+    // (tells the grid dispatcher whether the shared-row tile kernel applies); one 8-byte read-back
+    // per table build, i.e. per (t_eval, derivative order), never per evaluation
+    CUDA_TRY(D.table.spans.ensure(2 * sizeof(int32_t)));
+    CUDA_TRY(launch_group_span((const int32_t*)D.table.i0.p, D.n_eval, (int32_t*)D.table.spans.p, h->stream));
+    h->launches += D.n_eval ? 1 : 0;
+    int32_t sp[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(sp, D.table.spans.p, sizeof sp, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    D.table.span2 = sp[0];
+    D.table.span4 = sp[1];
     D.table.order = order;
     return DIND_OK;
 }

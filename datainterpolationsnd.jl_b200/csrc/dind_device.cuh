@@ -90,6 +90,8 @@ struct DimParams {
     int32_t width;         // stencil width: 1 Constant, 2 Linear, degree+1 BSpline
     int32_t n_u;           // size(u, dim)
     int32_t order;         // derivative order requested for this dimension
+    int32_t group_span2;   // grid tables: max over aligned groups of 2 / 4 grid coordinates of
+    int32_t group_span4;   //   (max i0 - min i0); -1 = unknown
 };
 
 template <typename T>
