@@ -27,11 +27,13 @@ import numpy as np
 
 from . import _lib
 from ._lib import DindError, shard_range  # noqa: F401
+from .parallel import gather_grid, gather_unstructured, shard_t_eval  # noqa: F401
 
 __all__ = [
     "NDInterpolation", "LinearInterpolationDimension", "ConstantInterpolationDimension",
     "BSplineInterpolationDimension", "NURBSWeights", "EmptyCache", "eval_unstructured",
     "eval_unstructured_", "eval_grid", "eval_grid_", "DindError", "f_empty", "shard_range",
+    "shard_t_eval", "gather_unstructured", "gather_grid",
 ]
 
 
