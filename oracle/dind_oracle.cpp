@@ -248,14 +248,18 @@ PointStatus interpolate_constant(T* out, int64_t out_stride, const Interp<T>& A,
 // src/interpolation_methods.jl:69-98 (BSpline) and :101-141 (NURBS, when A.weights != null).
 template <class T>
 PointStatus interpolate_bspline(T* out, int64_t out_stride, const Interp<T>& A, const T* t,
-                                const int64_t* idx, const int* orders) {
+                                const int64_t* idx, const int* orders, const T* const* cached_basis) {
     const int N = A.n_in;
     for (int64_t c = 0; c < A.n_comp; ++c) out[c * out_stride] = T(0);   // :79 / :112
     T B[MAXN][MAXDEG + 1];
     int deg[MAXN];
     for (int i = 0; i < N; ++i) {                                        // :80-83 (spline_utils.jl:149-162)
         deg[i] = A.dims[i].degree;
-        get_basis_function_values(A.dims[i], t[i], idx[i], orders[i], B[i]);
+        if (cached_basis && cached_basis[i]) {                           // view(basis_function_eval, k, :, r+1), spline_utils.jl:118-146
+            for (int k = 0; k <= deg[i]; ++k) B[i][k] = cached_basis[i][k];
+        } else {                                                         // on the fly, spline_utils.jl:64-98
+            get_basis_function_values(A.dims[i], t[i], idx[i], orders[i], B[i]);
+        }
     }
     T denom = T(0);                                                      // :117
     int I[MAXN];
@@ -295,7 +299,7 @@ PointStatus interpolate_bspline(T* out, int64_t out_stride, const Interp<T>& A, 
 // ---------------------------------------------------------------------------
 template <class T>
 PointStatus interpolate_mixed(T* out, int64_t out_stride, const Interp<T>& A, const T* t,
-                              const int64_t* idx, const int* orders) {
+                              const int64_t* idx, const int* orders, const T* const* cached_basis) {
     const int N = A.n_in;
     bool const_deriv = false, on_knot = false;
     for (int i = 0; i < N; ++i) {
@@ -332,7 +336,8 @@ PointStatus interpolate_mixed(T* out, int64_t out_stride, const Interp<T>& A, co
             else { W[i][0] = T(0); W[i][1] = T(0); }
         } else {
             width[i] = d.degree + 1; first[i] = idx[i] - d.degree;
-            get_basis_function_values(d, t[i], idx[i], orders[i], W[i]);
+            if (cached_basis && cached_basis[i]) for (int k = 0; k <= d.degree; ++k) W[i][k] = cached_basis[i][k];
+            else get_basis_function_values(d, t[i], idx[i], orders[i], W[i]);
         }
     }
     T denom = T(0);
@@ -357,40 +362,74 @@ PointStatus interpolate_mixed(T* out, int64_t out_stride, const Interp<T>& A, co
 
 template <class T>
 inline PointStatus interpolate(T* out, int64_t out_stride, const Interp<T>& A, const T* t,
-                               const int64_t* idx, const int* orders, int homogeneous_kind) {
+                               const int64_t* idx, const int* orders, int homogeneous_kind,
+                               const T* const* cached_basis) {
     switch (homogeneous_kind) {
         case LINEAR: return interpolate_linear(out, out_stride, A, t, idx, orders);
         case CONSTANT: return interpolate_constant(out, out_stride, A, t, idx, orders);
-        case BSPLINE: return interpolate_bspline(out, out_stride, A, t, idx, orders);
-        default: return interpolate_mixed(out, out_stride, A, t, idx, orders);
+        case BSPLINE: return interpolate_bspline(out, out_stride, A, t, idx, orders, cached_basis);
+        default: return interpolate_mixed(out, out_stride, A, t, idx, orders, cached_basis);
     }
 }
 
 // src/interpolation_parallel.jl:105-138 — eval_kernel, one "work item" per output point;
 // the KA CPU backend's static split of ndrange over threads is mirrored by
 // `omp for schedule(static)`.
+double g_last_eval_seconds = 0.0;   // duration of the last eval_kernel loop (caches excluded)
+
 template <class T>
 void eval_driver(T* out, const Interp<T>& A, const int* orders, bool grid, int kind, int nthreads) {
     const int N = A.n_in;
     int64_t npts = 1;
     if (grid) for (int i = 0; i < N; ++i) npts *= A.dims[i].n_eval;
     else npts = A.dims[0].n_eval;
-    (void)nthreads;
+    const int nt =
 #ifdef _OPENMP
-#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : omp_get_max_threads())
+        nthreads > 0 ? nthreads : omp_get_max_threads();
+#else
+        1;
+    (void)nthreads;
+#endif
+    // The per-dimension caches the reference fills at CONSTRUCTION time, outside eval_*:
+    // idx_eval (set_eval_idx!, interpolation_utils.jl:143-161) and, for BSpline dimensions,
+    // basis_function_eval for the requested derivative order (set_basis_function_eval!,
+    // spline_utils.jl:164-191; the reference fills orders 0..max, only the one read is built here).
+    std::vector<int64_t> idx_cache[MAXN];
+    std::vector<T> basis_cache[MAXN];
+    for (int i = 0; i < N; ++i) {
+        const Dim<T>& d = A.dims[i];
+        idx_cache[i].resize((size_t)d.n_eval);
+        const int W = d.degree + 1;
+        if (d.kind == BSPLINE) basis_cache[i].resize((size_t)d.n_eval * W);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nt)
+#endif
+        for (int64_t k = 0; k < d.n_eval; ++k) {
+            idx_cache[i][k] = get_idx(d, d.t_eval[k]);
+            if (d.kind == BSPLINE) get_basis_function_values(d, d.t_eval[k], idx_cache[i][k], orders[i], &basis_cache[i][k * W]);
+        }
+    }
+#ifdef _OPENMP
+    const double t0 = omp_get_wtime();
+#pragma omp parallel for schedule(static) num_threads(nt)
 #endif
     for (int64_t k = 0; k < npts; ++k) {
         T t[MAXN];
         int64_t idx[MAXN];
+        const T* bc[MAXN];
         int64_t rem = k;
         for (int i = 0; i < N; ++i) {
             int64_t ki = k;
             if (grid) { ki = rem % A.dims[i].n_eval; rem /= A.dims[i].n_eval; }
             t[i] = A.dims[i].t_eval[ki];                                 // :117 / :120
-            idx[i] = get_idx(A.dims[i], t[i]);                           // cached idx_eval[k] (:118/:121) == get_idx(t_eval[k])
+            idx[i] = idx_cache[i][ki];                                   // :118 / :121
+            bc[i] = A.dims[i].kind == BSPLINE ? &basis_cache[i][ki * (A.dims[i].degree + 1)] : nullptr;
         }
-        interpolate(out + k, npts, A, t, idx, orders, kind);             // :128-137
+        interpolate(out + k, npts, A, t, idx, orders, kind, bc);         // :128-137
     }
+#ifdef _OPENMP
+    g_last_eval_seconds = omp_get_wtime() - t0;
+#endif
 }
 
 // --- plumbing from the flat C arguments to Interp<T> -----------------------
@@ -534,6 +573,10 @@ int dindo_expand_knots(int dtype, const void* t, int64_t n_t, int degree, const 
     if (dtype == 0) return knots_T<float>(t, n_t, degree, mult, out, n_out);
     return knots_T<double>(t, n_t, degree, mult, out, n_out);
 }
+
+// seconds spent in the last evaluation loop proper (the reference's eval_* call: caches are
+// built by the constructors and are not part of it)
+double dindo_last_eval_seconds(void) { return g_last_eval_seconds; }
 
 int dindo_max_threads(void) {
 #ifdef _OPENMP

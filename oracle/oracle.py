@@ -42,7 +42,13 @@ def lib():
         _lib.dindo_basis.restype = C.c_int
         _lib.dindo_expand_knots.restype = C.c_int
         _lib.dindo_max_threads.restype = C.c_int
+        _lib.dindo_last_eval_seconds.restype = C.c_double
     return _lib
+
+
+def last_eval_seconds() -> float:
+    """Duration of the last evaluation loop proper (idx/basis cache construction excluded, as in the reference)."""
+    return float(lib().dindo_last_eval_seconds())
 
 
 def max_threads() -> int:
