@@ -239,8 +239,10 @@ def run_gpu(args, wl, rank, world, local_rank):
         itp = D.NDInterpolation(ud, dims, device=local_rank, stream=stream.cuda_stream)
         out = D.f_empty((n,) + shape[len(wl.kinds):], wl.dtype, dev)
 
+        uflags = 1 | (16 if args.sorted else 0)   # DIND_FLAG_ASYNC | DIND_FLAG_CELL_SORTED
+
         def step(i):
-            D.eval_unstructured_(out, itp, flags=1)
+            D.eval_unstructured_(out, itp, flags=uflags)
 
     def barrier():
         if world > 1:
@@ -320,7 +322,7 @@ def run_gpu(args, wl, rank, world, local_rank):
         "config": {"workload": wl.name, "points_per_step_per_gpu": wl.points_per_step(),
                    "sharding": ("slab along the last grid axis" if wl.grid else "contiguous index range") + ", u/knots replicated, no collective",
                    "l2": "working set exceeds L2 (126 MB): output streamed, u rotates over 4 buffers" if wl.grid else "t_eval + out exceed L2",
-                   "kernel": kernel},
+                   "kernel": kernel, "point_order": ("iid random, evaluated through the cell-sorted plan" if args.sorted else "iid random") if not wl.grid else "grid"},
         "e2e": {"value": round(pts_step_all / (e2e_ms * 1e-3) / 1e9, 4), "unit": "Gpoints/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "host (pinned) buffers through the public API; synchronous call incl. H2D + kernel + D2H"},
@@ -420,6 +422,7 @@ def main():
     ap.add_argument("--full", action="store_true", help="full-size point counts for c3 / c5")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink c2 (debugging only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sorted", action="store_true", help="unstructured workloads: evaluate through the cell-sorted plan")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", 0))

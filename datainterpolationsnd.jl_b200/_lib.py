@@ -11,7 +11,7 @@ OK = 0
 ERR_INVALID_ARGUMENT, ERR_SIZE_MISMATCH, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6
 F32, F64 = 0, 1
 LINEAR, CONSTANT, BSPLINE = 0, 1, 2
-FLAG_ASYNC, FLAG_COPY, FLAG_CACHED_IDX, FLAG_GENERIC = 1, 2, 4, 8
+FLAG_ASYNC, FLAG_COPY, FLAG_CACHED_IDX, FLAG_GENERIC, FLAG_CELL_SORTED = 1, 2, 4, 8, 16
 MAX_DIMS, MAX_DEGREE = 8, 7
 
 # every symbol include/dind.h declares: (name, restype, argtypes)

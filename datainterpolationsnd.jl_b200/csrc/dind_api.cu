@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -112,6 +113,11 @@ struct dind_interp_s {
     DevBuf w_owned;
     DevBuf uw;          // u pre-multiplied by the weights
     bool uw_valid = false;
+    // cell-sorted plan for eval_unstructured (dind_plan.cu)
+    bool plan_valid = false;
+    int64_t plan_n = 0;
+    DevBuf plan_perm;
+    DevBuf plan_t[MAXN];
     // staging
     DevBuf out_stage;
     DevBuf pts_stage[MAXN];
@@ -354,6 +360,36 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         }
     }
 
+    if (!grid && have_idx_cache && (flags & DIND_FLAG_CELL_SORTED)) {
+        if (n_points >= (1LL << 32) || h->comp_stride >= (1LL << 32))
+            return fail(DIND_ERR_UNSUPPORTED, "DIND_FLAG_CELL_SORTED needs fewer than 2^32 points and u elements per component");
+        if (!h->plan_valid || h->plan_n != n_points) {
+            CUDA_TRY(h->plan_perm.ensure((size_t)n_points * sizeof(uint32_t)));
+            T* ts[MAXN];
+            for (int d = 0; d < N; ++d) {
+                CUDA_TRY(h->plan_t[d].ensure((size_t)n_points * sizeof(T)));
+                ts[d] = (T*)h->plan_t[d].p;
+            }
+            size_t scratch_bytes = 0;
+            CUDA_TRY(plan_sort_points<T>(P, nullptr, ts, nullptr, &scratch_bytes, h->stream));
+            DevBuf scratch;
+            CUDA_TRY(scratch.ensure(scratch_bytes));
+            cudaError_t pe = plan_sort_points<T>(P, (uint32_t*)h->plan_perm.p, ts, scratch.p, &scratch_bytes, h->stream);
+            if (pe == cudaSuccess) pe = cudaStreamSynchronize(h->stream);
+            scratch.release();
+            CUDA_TRY(pe);
+            h->launches += 2 + N;
+            h->plan_valid = true;
+            h->plan_n = n_points;
+        }
+        for (int d = 0; d < N; ++d) {
+            P.dim[d].t_eval = (const T*)h->plan_t[d].p;
+            P.dim[d].idx_eval = nullptr;
+        }
+        P.use_cached_idx = 0;
+        P.perm = (const uint32_t*)h->plan_perm.p;
+    }
+
     bool handled = false;
     cudaError_t err = cudaSuccess;
     const char* name = nullptr;
@@ -475,6 +511,8 @@ int dind_destroy(dind_handle_t h) {
         h->pts_stage[d].release();
     }
     h->u_owned.release(); h->w_owned.release(); h->uw.release(); h->out_stage.release();
+    h->plan_perm.release();
+    for (int d = 0; d < MAXN; ++d) h->plan_t[d].release();
     delete h;
     return DIND_OK;
 }
@@ -556,6 +594,7 @@ int dind_set_dim(dind_handle_t h, int dim, int kind, const void* t, int64_t n_t,
     if (rc) return rc;
     D.set = true;
     D.invalidate_caches();
+    h->plan_valid = false;
     return DIND_OK;
 }
 
@@ -583,6 +622,7 @@ int dind_set_t_eval(dind_handle_t h, int dim, const void* t_eval, int64_t n_eval
     D.max_deriv = max_derivative_order_eval;
     D.teval_set = true;
     D.invalidate_caches();
+    h->plan_valid = false;
     return DIND_OK;
 }
 
@@ -617,6 +657,7 @@ int dind_set_u(dind_handle_t h, const void* u, const int64_t* dims, int ndims, u
         if (!is_device_ptr(u)) CUDA_TRY(cudaStreamSynchronize(h->stream));   // pageable source may be reused by the caller
         h->d_u = h->u_owned.p;
     }
+    if (!h->u_set || h->u_dims.size() != (size_t)ndims || !std::equal(dims, dims + ndims, h->u_dims.begin())) h->plan_valid = false;
     h->u_dims.assign(dims, dims + ndims);
     h->comp_stride = comp_stride;
     h->n_comp = n_comp;

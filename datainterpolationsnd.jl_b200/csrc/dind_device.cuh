@@ -109,6 +109,7 @@ struct EvalParams {
     int32_t const_deriv;   // some Constant dimension has derivative order > 0
     int32_t zero_result;   // Linear with order > 1 somewhere: result is identically zero
     int32_t use_cached_idx;
+    const uint32_t* perm;  // cell-sorted plan: point k of the (sorted) t_eval arrays is original point perm[k]; null = identity
 };
 
 // ---- Cox–de Boor in registers (src/spline_utils.jl:24-114), runtime degree ---------------

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(BLOCK) eval_generic_kernel(const __grid_consta
     const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (k >= P.n_points) return;
     const int N = P.n_in;
+    const int64_t ko = (!GRID && P.perm) ? (int64_t)P.perm[k] : k;   // output position (cell-sorted plan)
     int i0[MAXN];
     T w[MAXN][MAXW];
     bool any_on_knot = false;
@@ -111,14 +112,14 @@ __global__ void __launch_bounds__(BLOCK) eval_generic_kernel(const __grid_consta
         // unchanged — zero for scalar output (fresh make_out), untouched memory for N_out > 0.
         if (any_on_knot) {
             const T nan = T(0) / T(0);
-            for (int c = 0; c < P.n_comp; ++c) P.out[k + c * P.out_comp_stride] = nan;
+            for (int c = 0; c < P.n_comp; ++c) P.out[ko + c * P.out_comp_stride] = nan;
         } else if (P.scalar_out) {
-            P.out[k] = T(0);
+            P.out[ko] = T(0);
         }
         return;
     }
     if (P.zero_result) {  // Linear with a derivative order > 1 (:10)
-        for (int c = 0; c < P.n_comp; ++c) P.out[k + c * P.out_comp_stride] = T(0);
+        for (int c = 0; c < P.n_comp; ++c) P.out[ko + c * P.out_comp_stride] = T(0);
         return;
     }
     int64_t base = 0;
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(BLOCK) eval_generic_kernel(const __grid_consta
             }
         }
         for (int j = 0; j < CB; ++j)
-            if (c0 + j < P.n_comp) P.out[k + (int64_t)(c0 + j) * P.out_comp_stride] = P.wts ? acc[j] / den : acc[j];
+            if (c0 + j < P.n_comp) P.out[ko + (int64_t)(c0 + j) * P.out_comp_stride] = P.wts ? acc[j] / den : acc[j];
     }
 }
 

@@ -19,6 +19,14 @@ template <typename T> cudaError_t launch_premultiply(const T* u, const T* w, T* 
 // generic evaluation: any N_in <= MAXN, any kinds, any degree <= MAXW-1
 template <typename T> cudaError_t launch_eval_generic(const EvalParams<T>& P, bool grid, cudaStream_t s);
 
+// Cell-sorted plan for eval_unstructured (dind_plan.cu): perm = point indices sorted by the
+// offset of their first stencil node in u (points of one cell become neighbours, cells follow
+// memory order), t_sorted[d] = t_eval[d][perm].  scratch_bytes in/out: pass *scratch = nullptr to
+// query the scratch size.
+template <typename T>
+cudaError_t plan_sort_points(const EvalParams<T>& P, uint32_t* perm, T* const* t_sorted, void* scratch,
+                             size_t* scratch_bytes, cudaStream_t s);
+
 // Specialised kernels.  Return true when they handled the evaluation (err holds the launch
 // status), false when the configuration is outside their envelope.
 template <typename T> bool try_eval_fast_unstructured(const EvalParams<T>& P, cudaStream_t s, const char** name,

@@ -64,7 +64,12 @@ extern "C" {
 #define DIND_FLAG_COPY 2u        /* copy device data instead of borrowing it                           */
 #define DIND_FLAG_CACHED_IDX 4u  /* eval_unstructured: read the idx_eval cache instead of searching   */
 #define DIND_FLAG_GENERIC 8u     /* force the generic (any-N, any-degree) kernels; testing/reference  */
-#define DIND_FLAG_NO_SORT_CHECK 16u /* reserved */
+#define DIND_FLAG_CELL_SORTED 16u /* eval_unstructured: evaluate through the cell-sorted plan — the point order
+                                    * that makes the stencil gathers warp-coherent.  The plan (a permutation and
+                                    * sorted copies of t_eval: n*(4 + n_in*sizeof(T)) bytes) is built on first use
+                                    * and cached until t_eval, the knots or size(u) change — the analogue of the
+                                    * reference's idx_eval / basis_function_eval caches.  Results are written to
+                                    * their original positions: `out` is identical to the unsorted evaluation. */
 
 #define DIND_MAX_DIMS 8   /* N_in <= 8 */
 #define DIND_MAX_DEGREE 7 /* B-spline degree <= 7 */

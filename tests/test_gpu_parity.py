@@ -378,3 +378,37 @@ def test_device_tensors_zero_copy_and_new_u(D):
     D.eval_grid_(out2, itp)
     H.assert_close(out2.cpu().numpy(), O.evaluate(["linear"] * 3, ts, u1, xs, grid=True), np.float32)
     itp.close()
+
+
+# ---- cell-sorted plan: same numbers, original output positions ---------------------------------------
+CELL_SORTED = 16
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", [1, 3, 5, 9, 11])
+def test_cell_sorted_plan_is_bit_identical(D, dtype, case):
+    kinds, degrees, n_knots, out_dims, orders_list = CASES[case]
+    rng = np.random.default_rng(400 + case)
+    ts, u, _ = _case(rng, kinds, degrees, n_knots, out_dims, dtype)
+    xs = H.zipped_queries(rng, ts, 20000, dtype)
+    dims = H.make_dims(D, kinds, ts, xs, degrees, None, max_deriv=[1] * len(kinds))
+    itp = D.NDInterpolation(u, dims)
+    for orders in orders_list:
+        if any(o > 1 for o in orders):
+            continue
+        if "constant" in kinds and any(o > 0 for o in orders) and out_dims:
+            a = np.full((xs[0].size,) + tuple(out_dims), 7.25, dtype=dtype, order="F")
+            b = a.copy(order="F")
+            D.eval_unstructured_(a, itp, derivative_orders=orders)
+            D.eval_unstructured_(b, itp, derivative_orders=orders, flags=CELL_SORTED)
+        else:
+            a = D.eval_unstructured(itp, derivative_orders=orders)
+            b = D.eval_unstructured(itp, derivative_orders=orders, flags=CELL_SORTED)
+        assert np.array_equal(a, b, equal_nan=True)
+    # a new u of the same shape re-uses the plan; new t_eval rebuilds it
+    u2 = rng.random(u.shape).astype(dtype)
+    itp.set_u(u2)
+    a = D.eval_unstructured(itp)
+    b = D.eval_unstructured(itp, flags=CELL_SORTED)
+    assert np.array_equal(a, b, equal_nan=True)
+    itp.close()
