@@ -55,16 +55,11 @@ class Workload:
         raise NotImplementedError
 
 
-class C2(Workload):
-    """3-D trilinear, u 256^3 F32 -> 512^3 grid (per GPU), slab-sharded along axis 3."""
-    name = "c2: 3-D trilinear u=256^3 Float32, eval_grid! onto 512^3 (cached idx, new u each step)"
-    key = "c2"
-    dtype = np.float32
-    dtype_name = "f32"
+class Grid(Workload):
+    """eval_grid! workloads: slab-sharded along the last interpolation axis."""
     grid = True
-    n_u = (256, 256, 256)
-    n_grid = (512, 512, 512)   # per GPU
-    n_u_buffers = 4            # u rotates over 4 x 67 MB buffers so it is never L2-resident at step start
+    nurbs = False
+    n_u_buffers = 4            # u rotates over several buffers so it is never L2-resident at step start
 
     def __init__(self, scale=1.0):
         if scale != 1.0:
@@ -75,21 +70,64 @@ class C2(Workload):
         return int(np.prod(self.n_grid))
 
     def alg_bytes(self):
-        # out write (4 B/pt) + one read of u per launch
-        return self.points_per_step() * 4 + int(np.prod(self.n_u)) * 4
+        # out write + one read of u (and of the NURBS weights) per launch
+        esz = np.dtype(self.dtype).itemsize
+        return self.points_per_step() * esz + int(np.prod(self.n_u)) * esz * (2 if self.nurbs else 1)
+
+    def n_knots(self, d):
+        return self.n_u[d] - self.degrees[d] + 1 if self.kinds[d] == "bspline" else self.n_u[d]
 
     def build(self, rank, world):
         rng = np.random.default_rng(1234)
-        self.ts = [knots_1d(rng, n, self.dtype) for n in self.n_u]
-        # global grid: axis 3 has n_grid[2] * world points, rank r owns slab r
+        nd = len(self.n_u)
+        self.ts = [knots_1d(rng, self.n_knots(d), self.dtype) for d in range(nd)]
+        # global grid: the last axis has n_grid[-1] * world points, rank r owns slab r
         self.t_evals = []
         for d, (t, g) in enumerate(zip(self.ts, self.n_grid)):
-            if d == 2:
+            if d == nd - 1:
                 full = np.linspace(t[0], t[-1], g * world).astype(self.dtype)
                 self.t_evals.append(full[rank * g:(rank + 1) * g])
             else:
                 self.t_evals.append(np.linspace(t[0], t[-1], g).astype(self.dtype))
-        self.u_rng = np.random.default_rng(99 + rank)
+
+    def make_dims(self, D, t_evals):
+        dims = []
+        for k, p, t, x in zip(self.kinds, self.degrees, self.ts, t_evals):
+            if k == "linear":
+                dims.append(D.LinearInterpolationDimension(t, t_eval=x))
+            elif k == "constant":
+                dims.append(D.ConstantInterpolationDimension(t, left=True, t_eval=x))
+            else:
+                dims.append(D.BSplineInterpolationDimension(t, p, t_eval=x))
+        return tuple(dims)
+
+
+class C2(Grid):
+    """3-D trilinear, u 256^3 F32 -> 512^3 grid (per GPU)."""
+    name = "c2: 3-D trilinear u=256^3 Float32, eval_grid! onto 512^3 (cached idx, new u each step)"
+    key, dtype, dtype_name = "c2", np.float32, "f32"
+    kinds, degrees = ("linear",) * 3, (0, 0, 0)
+    n_u = (256, 256, 256)
+    n_grid = (512, 512, 512)   # per GPU
+
+
+class C4(Grid):
+    """4-D degree-2 NURBS, u 64^4 + weights 64^4 F64 -> 128^4 grid (per GPU)."""
+    name = "c4: 4-D NURBS (degree 2, NURBSWeights) u=64^4 Float64, eval_grid! onto 128^4"
+    key, dtype, dtype_name = "c4", np.float64, "f64"
+    kinds, degrees = ("bspline",) * 4, (2, 2, 2, 2)
+    n_u = (64,) * 4
+    n_grid = (128,) * 4
+    nurbs = True
+    n_u_buffers = 2
+
+
+class C4b(C4):
+    """Variant with mixed kinds (no reference semantics): axis 3 is Constant(left=true)."""
+    name = "c4b: 4-D NURBS-weighted, axes (BSpline2, BSpline2, Constant(left=true), BSpline2) u=64^4 Float64 -> 128^4"
+    key = "c4b"
+    kinds, degrees = ("bspline", "bspline", "constant", "bspline"), (2, 2, 0, 2)
+    nurbs = False   # NURBS weights need all-BSpline dimensions (as in the reference's validate_cache)
 
 
 class Unstructured(Workload):
@@ -211,13 +249,19 @@ def run_gpu(args, wl, rank, world, local_rank):
     gen = torch.Generator(device=dev)
     gen.manual_seed(1000 + rank)
     if wl.grid:
-        dims = tuple(D.LinearInterpolationDimension(t, t_eval=to_dev(x)) for t, x in zip(wl.ts, wl.t_evals))
+        dims = wl.make_dims(D, [to_dev(x) for x in wl.t_evals])
+        rev = tuple(reversed(range(len(wl.n_u))))
         u_bufs = []
         for _ in range(wl.n_u_buffers):
             ub = D.f_empty(wl.n_u, wl.dtype, dev)
-            ub.copy_(torch.rand(wl.n_u[::-1], generator=gen, device=dev, dtype=tdt).permute(2, 1, 0))
+            ub.copy_(torch.rand(wl.n_u[::-1], generator=gen, device=dev, dtype=tdt).permute(*rev))
             u_bufs.append(ub)
-        itp = D.NDInterpolation(u_bufs[0], dims, device=local_rank, stream=stream.cuda_stream)
+        cache = None
+        if wl.nurbs:
+            wts = D.f_empty(wl.n_u, wl.dtype, dev)
+            wts.copy_((torch.rand(wl.n_u[::-1], generator=gen, device=dev, dtype=tdt) + 0.5).permute(*rev))
+            cache = D.NURBSWeights(wts)
+        itp = D.NDInterpolation(u_bufs[0], dims, cache=cache, device=local_rank, stream=stream.cuda_stream)
         out = D.f_empty(wl.n_grid, wl.dtype, dev)
 
         def step(i):
@@ -269,9 +313,10 @@ def run_gpu(args, wl, rank, world, local_rank):
     if wl.grid:
         u_host = [torch.rand(wl.n_u[::-1], dtype=tdt).pin_memory() for _ in range(2)]
         out_host = torch.empty(wl.n_grid[::-1], dtype=tdt).pin_memory()
-        u_np = [t.numpy().transpose(2, 1, 0) for t in u_host]          # column-major views of the pinned buffers
-        out_np = out_host.numpy().transpose(2, 1, 0)
-        itp_h = D.NDInterpolation(u_np[0], tuple(D.LinearInterpolationDimension(t, t_eval=x) for t, x in zip(wl.ts, wl.t_evals)),
+        u_np = [t.numpy().transpose(*rev) for t in u_host]          # column-major views of the pinned buffers
+        out_np = out_host.numpy().transpose(*rev)
+        itp_h = D.NDInterpolation(u_np[0], wl.make_dims(D, wl.t_evals),
+                                  cache=None if not wl.nurbs else D.NURBSWeights(wts),
                                   device=local_rank, stream=stream.cuda_stream)
         n_e2e = max(2, min(args.steps, 5))
         for i in range(2):
@@ -283,7 +328,8 @@ def run_gpu(args, wl, rank, world, local_rank):
             D.eval_grid_(out_np, itp_h)      # kernel + D2H of the result, synchronous like the reference
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
-        h2d, d2h = int(np.prod(wl.n_u)) * 4, wl.points_per_step() * 4
+        esz = np.dtype(wl.dtype).itemsize
+        h2d, d2h = int(np.prod(wl.n_u)) * esz, wl.points_per_step() * esz
         itp_h.close()
     else:
         n = out.shape[0]
@@ -321,7 +367,7 @@ def run_gpu(args, wl, rank, world, local_rank):
         "vs_baseline": None, "dtype": wl.dtype_name, "data": "synthetic",
         "config": {"workload": wl.name, "points_per_step_per_gpu": wl.points_per_step(),
                    "sharding": ("slab along the last grid axis" if wl.grid else "contiguous index range") + ", u/knots replicated, no collective",
-                   "l2": "working set exceeds L2 (126 MB): output streamed, u rotates over 4 buffers" if wl.grid else "t_eval + out exceed L2",
+                   "l2": f"working set exceeds L2 (126 MB): output streamed, u rotates over {wl.n_u_buffers} buffers" if wl.grid else "t_eval + out exceed L2",
                    "kernel": kernel, "point_order": ("iid random, evaluated through the cell-sorted plan" if args.sorted else "iid random") if not wl.grid else "grid"},
         "e2e": {"value": round(pts_step_all / (e2e_ms * 1e-3) / 1e9, 4), "unit": "Gpoints/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -353,18 +399,19 @@ def cpu_sample(wl, seconds_target=12.0, nthreads=0):
     if wl.grid:
         u = rng.random(wl.n_u, dtype=np.float32).astype(wl.dtype)
         u = np.asfortranarray(u)
+        wts = np.asfortranarray(0.5 + rng.random(wl.n_u, dtype=np.float32).astype(wl.dtype)) if wl.nurbs else None
         k = 2
         sample = None
         while True:
-            te = [wl.t_evals[0], wl.t_evals[1], wl.t_evals[2][:k]]
+            te = list(wl.t_evals[:-1]) + [wl.t_evals[-1][:k]]
             t0 = time.perf_counter()
-            O.evaluate(["linear"] * 3, wl.ts, u, te, grid=True, nthreads=nthreads)
+            O.evaluate(list(wl.kinds), wl.ts, u, te, degrees=list(wl.degrees), weights=wts, grid=True, nthreads=nthreads)
             dt = time.perf_counter() - t0
             pts = int(np.prod([len(x) for x in te]))
-            sample = (pts, O.last_eval_seconds(), f"{len(te[0])}x{len(te[1])}x{k} slab of the {wl.n_grid} grid, full u; eval loop only (idx cache prebuilt, as the reference does at construction)")
-            if dt > seconds_target / 3 or k >= len(wl.t_evals[2]):
+            sample = (pts, O.last_eval_seconds(), f"{'x'.join(str(len(x)) for x in te)} slab of the {wl.n_grid} grid, full u; eval loop only (idx cache prebuilt, as the reference does at construction)")
+            if dt > seconds_target / 3 or k >= len(wl.t_evals[-1]):
                 break
-            k = min(len(wl.t_evals[2]), max(k * 2, int(k * seconds_target / 2 / max(dt, 1e-3))))
+            k = min(len(wl.t_evals[-1]), max(k * 2, int(k * seconds_target / 2 / max(dt, 1e-3))))
         return sample[0] / sample[1] / 1e9, nthreads, sample[2]
     shape = tuple(wl.n_u)
     u = np.asfortranarray(rng.random(shape).astype(wl.dtype))
@@ -403,6 +450,10 @@ def run_reference(args, wl, rank, world):
 def make_workload(args):
     if args.workload == "c2":
         return C2(args.scale)
+    if args.workload == "c4":
+        return C4(args.scale)
+    if args.workload == "c4b":
+        return C4b(args.scale)
     if args.workload == "c1":
         return C1()
     if args.workload == "c3":

@@ -74,7 +74,9 @@ struct DimState {
     std::vector<double> knots;      // t, or knots_all for BSpline
     int width = 0;
     int64_t n_u = 0;                // expected size(u, dim)
-    DevBuf d_knots, d_keys, d_recip;
+    DevBuf d_knots, d_keys, d_recip, d_lut;
+    int lut_n = 0;              // buckets of the search table (0 = none)
+    double lut_t0 = 0, lut_scale = 0;
     // t_eval
     bool teval_set = false;
     const void* d_teval = nullptr;  // device pointer (owned copy or borrowed)
@@ -89,7 +91,7 @@ struct DimState {
         table.order = -1;
     }
     void release() {
-        d_knots.release(); d_keys.release(); d_recip.release(); teval_owned.release();
+        d_knots.release(); d_keys.release(); d_recip.release(); d_lut.release(); teval_owned.release();
         d_idx.release(); table.i0.release(); table.w.release(); table.flag.release(); table.spans.release();
     }
 };
@@ -168,6 +170,22 @@ int upload_dim(dind_interp_s* h, DimState& D) {
     CUDA_TRY(cudaMemcpyAsync(D.d_knots.p, kn.data(), n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(D.d_keys.p, keys.data(), n * sizeof(K), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(D.d_recip.p, recip.data(), recip.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    // bucket table for the interval search: ~4 buckets per knot, built on the device with the
+    // same arithmetic the kernels use (dind_device.cuh: lut_bucket)
+    D.lut_n = 0;
+    if (n >= 8 && !getenv("DIND_NO_LUT")) {
+        int nb = 32;
+        while (nb < 4 * n && nb < 4096) nb <<= 1;
+        const T t0 = kn[0];
+        const T scale = T(nb) / (kn[n - 1] - kn[0]);
+        if (std::isfinite((double)scale) && scale > T(0)) {
+            CUDA_TRY(D.d_lut.ensure((size_t)(nb + 1) * sizeof(int32_t)));
+            CUDA_TRY(launch_lut<T>((const T*)D.d_knots.p, n, t0, scale, nb, (int32_t*)D.d_lut.p, h->stream));
+            D.lut_n = nb;
+            D.lut_t0 = (double)t0;
+            D.lut_scale = (double)scale;
+        }
+    }
     CUDA_TRY(cudaStreamSynchronize(h->stream));   // host vectors go out of scope
     return DIND_OK;
 }
@@ -185,6 +203,10 @@ DimParams<T> make_dim_params(const dind_interp_s* h, const DimState& D, int dim,
     P.tab_i0 = (const int32_t*)D.table.i0.p;
     P.tab_w = (const T*)D.table.w.p;
     P.tab_flag = (const uint8_t*)D.table.flag.p;
+    P.lut = D.lut_n ? (const int32_t*)D.d_lut.p : nullptr;
+    P.lut_t0 = (T)D.lut_t0;
+    P.lut_scale = (T)D.lut_scale;
+    P.lut_n = D.lut_n;
     P.n_eval = D.n_eval;
     int64_t stride = 1;
     for (int i = 0; i < dim; ++i) stride *= h->u_set ? h->u_dims[i] : 1;

@@ -68,6 +68,31 @@ __device__ __forceinline__ int count_lt(const K* __restrict__ keys, int n, K kx)
 
 __device__ __forceinline__ int clampi(int x, int lo, int hi) { return x > hi ? hi : (x < lo ? lo : x); }
 
+// ---- bucket-accelerated search ---------------------------------------------------------------
+// lut_bucket is monotone non-decreasing in x (subtraction of a constant, multiplication by a
+// positive constant, clamping and truncation all are), so for a query in bucket b every knot in
+// a lower bucket is < x and every knot in a higher bucket is > x: the exact count — still decided
+// by key comparisons only, hence bit-exact — lies in [lut[b], lut[b+1]], typically 0-2 knots.
+// The table is built on the device with this same function (dind_generic.cu: lut_kernel).
+template <typename T>
+__device__ __forceinline__ int lut_bucket(T x, T t0, T scale, int n_buckets) {
+    const T v = fmin(fmax((x - t0) * scale, T(0)), T(n_buckets - 1));   // NaN -> 0
+    return (int)v;
+}
+
+template <typename K, bool LE>
+__device__ __forceinline__ int count_range(const K* __restrict__ keys, int lo, int hi, K kx) {
+    int cnt = lo;
+    const int len = hi - lo;
+    if (len > 0) {
+        for (int step = 1 << (31 - __clz(len)); step > 0; step >>= 1) {
+            const int j = cnt + step;
+            if (j <= hi && (LE ? keys[j - 1] <= kx : keys[j - 1] < kx)) cnt = j;
+        }
+    }
+    return cnt;
+}
+
 // ---- per-dimension device descriptor ------------------------------------------------------
 template <typename T>
 struct DimParams {
@@ -90,6 +115,11 @@ struct DimParams {
     int32_t width;         // stencil width: 1 Constant, 2 Linear, degree+1 BSpline
     int32_t n_u;           // size(u, dim)
     int32_t order;         // derivative order requested for this dimension
+    // bucket table accelerating the interval search (null = plain binary search): for bucket
+    // b = lut_bucket(x), count_lt(x) and count_le(x) lie in [lut[b], lut[b + 1]]
+    const int32_t* lut;
+    T lut_t0, lut_scale;
+    int32_t lut_n;
     int32_t group_span2;   // grid tables: max over aligned groups of 2 / 4 grid coordinates of
     int32_t group_span4;   //   (max i0 - min i0); -1 = unknown
 };
@@ -111,6 +141,19 @@ struct EvalParams {
     int32_t use_cached_idx;
     const uint32_t* perm;  // cell-sorted plan: point k of the (sorted) t_eval arrays is original point perm[k]; null = identity
 };
+
+// count of knots < x (LE = false: searchsortedfirst - 1) or <= x (LE = true: searchsortedlast) in
+// Julia's isless order, through the bucket table when the dimension has one.
+template <typename T, bool LE>
+__device__ __forceinline__ int dim_count(const DimParams<T>& D, T x, typename KeyOf<T>::type kx) {
+    using K = typename KeyOf<T>::type;
+    const int n = D.n_knots;
+    if (D.lut == nullptr) return LE ? count_le(D.keys, n, kx) : count_lt(D.keys, n, kx);
+    if (kx == to_key(T(0) / T(0))) return n;   // NaN sorts after every knot
+    const int b = lut_bucket(x, D.lut_t0, D.lut_scale, D.lut_n);
+    const int lo = __ldg(D.lut + b), hi = __ldg(D.lut + b + 1);
+    return count_range<K, LE>(D.keys, lo, hi, kx);
+}
 
 // ---- Cox–de Boor in registers (src/spline_utils.jl:24-114), runtime degree ---------------
 // idx0: 0-based knot interval (reference idx - 1).  Writes p+1 values to w[0..p].
@@ -192,7 +235,7 @@ __device__ __forceinline__ void dim_stencil(const DimParams<T>& D, T x, int orde
     on_knot = false;
     if (D.kind == LINEAR) {
         // clamp(searchsortedfirst(t, x) - 1, 1, n-1): intervals (t[i], t[i+1]]
-        const int idx = cached_idx ? cached_idx : clampi(count_lt(D.keys, n, kx), 1, n - 1);
+        const int idx = cached_idx ? cached_idx : clampi(dim_count<T, false>(D, x, kx), 1, n - 1);
         idx1 = idx;
         const int c = idx - 1;
         const T t1 = D.knots[c], t2 = D.knots[c + 1], r = D.recip[c];
@@ -202,17 +245,17 @@ __device__ __forceinline__ void dim_stencil(const DimParams<T>& D, T x, int orde
         else { w[0] = T(0); w[1] = T(0); }                                  // :10
     } else if (D.kind == CONSTANT) {
         // clamp(searchsortedlast(t, x), 1, n-1): intervals [t[i], t[i+1])
-        const int cnt = count_le(D.keys, n, kx);
+        const int cnt = dim_count<T, true>(D, x, kx);
         const int idx = cached_idx ? cached_idx : clampi(cnt, 1, n - 1);
         idx1 = idx;
         i0 = (x >= D.knots[n - 1]) ? n - 1 : idx - 1;                       // :57-59
         w[0] = T(1);
         // :50 !isempty(searchsorted(t, x)); only consulted when some Constant dimension has a
         // derivative order > 0 (the reference then tests every dimension, not only that one)
-        on_knot = count_lt(D.keys, n, kx) < cnt;
+        on_knot = dim_count<T, false>(D, x, kx) < cnt;
     } else {
         const int p = D.degree;
-        const int idx = cached_idx ? cached_idx : clampi(count_le(D.keys, n, kx), p + 1, n - p - 1);
+        const int idx = cached_idx ? cached_idx : clampi(dim_count<T, true>(D, x, kx), p + 1, n - p - 1);
         idx1 = idx;
         i0 = idx - p - 1;                                                   // :87-89
         bspline_basis_rt<T>(D.knots, D.recip, n, p, idx - 1, x, order, w);

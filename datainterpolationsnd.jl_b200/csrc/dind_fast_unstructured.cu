@@ -45,7 +45,7 @@ __device__ __forceinline__ int stencil_ct(const DimParams<T>& D, T x, int cached
     const K kx = to_key(x);
     const int n = D.n_knots;
     if (W == 2 && D.kind == LINEAR) {
-        const int idx = cached_idx ? cached_idx : clampi(count_lt(D.keys, n, kx), 1, n - 1);
+        const int idx = cached_idx ? cached_idx : clampi(dim_count<T, false>(D, x, kx), 1, n - 1);
         const int c = idx - 1;
         const T t1 = __ldg(D.knots + c), t2 = __ldg(D.knots + c + 1), r = __ldg(D.recip + c);
         if (D.order == 0) { w[0] = (t2 - x) * r; w[1] = (x - t1) * r; }
@@ -53,7 +53,7 @@ __device__ __forceinline__ int stencil_ct(const DimParams<T>& D, T x, int cached
         return c;
     }
     // BSpline of degree W-1
-    const int idx = cached_idx ? cached_idx : clampi(count_le(D.keys, n, kx), W, n - W);
+    const int idx = cached_idx ? cached_idx : clampi(dim_count<T, true>(D, x, kx), W, n - W);
     bspline_basis_ct<T, W - 1>(D.knots, D.recip, n, idx - 1, x, D.order, w);
     return idx - W;
 }

@@ -55,6 +55,19 @@ __global__ void __launch_bounds__(BLOCK) axis_table_kernel(DimParams<T> D, int o
     for (int a = 0; a < D.width; ++a) tab_w[g * D.width + a] = w[a];
 }
 
+template <typename T>
+__global__ void __launch_bounds__(BLOCK) lut_kernel(const T* __restrict__ knots, int n, T t0, T scale, int nb, int32_t* __restrict__ lut) {
+    const int b = blockIdx.x * BLOCK + threadIdx.x;
+    if (b > nb) return;
+    // first knot whose bucket is >= b (buckets are non-decreasing along the sorted knots)
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if (lut_bucket(knots[m], t0, scale, nb) < b) lo = m + 1; else hi = m;
+    }
+    lut[b] = lo;
+}
+
 __global__ void __launch_bounds__(BLOCK) group_span_kernel(const int32_t* __restrict__ tab_i0, int64_t n, int32_t* __restrict__ spans) {
     const int64_t q = ((int64_t)blockIdx.x * BLOCK + threadIdx.x) * 4;
     if (q >= n) return;
@@ -179,6 +192,12 @@ cudaError_t launch_axis_table(const DimParams<T>& D, int order, int32_t* tab_i0,
     return cudaGetLastError();
 }
 
+template <typename T>
+cudaError_t launch_lut(const T* knots, int n_knots, T t0, T scale, int n_buckets, int32_t* lut, cudaStream_t s) {
+    lut_kernel<T><<<blocks_for(n_buckets + 1, BLOCK), BLOCK, 0, s>>>(knots, n_knots, t0, scale, n_buckets, lut);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_group_span(const int32_t* tab_i0, int64_t n, int32_t* spans, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(spans, 0, 2 * sizeof(int32_t), s);
     if (e != cudaSuccess || n == 0) return e;
@@ -203,6 +222,7 @@ cudaError_t launch_eval_generic(const EvalParams<T>& P, bool grid, cudaStream_t 
 }
 
 #define DIND_INSTANTIATE(T)                                                                                    \
+    template cudaError_t launch_lut<T>(const T*, int, T, T, int, int32_t*, cudaStream_t);                      \
     template cudaError_t launch_idx<T>(const DimParams<T>&, int32_t*, cudaStream_t);                          \
     template cudaError_t launch_basis_cache<T>(const DimParams<T>&, int, T*, cudaStream_t);                   \
     template cudaError_t launch_axis_table<T>(const DimParams<T>&, int, int32_t*, T*, uint8_t*, cudaStream_t); \

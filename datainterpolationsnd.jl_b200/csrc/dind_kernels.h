@@ -12,6 +12,8 @@ template <typename T> cudaError_t launch_basis_cache(const DimParams<T>& D, int 
 // per-axis stencil tables for grid evaluation at one derivative order.
 template <typename T> cudaError_t launch_axis_table(const DimParams<T>& D, int order, int32_t* tab_i0, T* tab_w,
                                                     uint8_t* tab_flag, cudaStream_t s);
+// bucket table of the interval search: lut[b] = #{i : lut_bucket(knots[i]) < b}, b = 0..n_buckets
+template <typename T> cudaError_t launch_lut(const T* knots, int n_knots, T t0, T scale, int n_buckets, int32_t* lut, cudaStream_t s);
 // spans[0] / spans[1] = max over aligned groups of 2 / 4 grid coordinates of (max i0 - min i0)
 cudaError_t launch_group_span(const int32_t* tab_i0, int64_t n, int32_t* spans, cudaStream_t s);
 // uw[i + c*n] = u[i + c*n] * w[i]  (NURBS numerator, src/interpolation_methods.jl:124-131)
