@@ -62,8 +62,7 @@ struct DevBuf {
 
 struct AxisTable {
     int order = -1;
-    DevBuf i0, w, flag, spans;
-    int span2 = -1, span4 = -1;   // see DimParams::group_span2/4
+    DevBuf i0, w, flag;
 };
 
 struct DimState {
@@ -92,7 +91,7 @@ struct DimState {
     }
     void release() {
         d_knots.release(); d_keys.release(); d_recip.release(); d_lut.release(); teval_owned.release();
-        d_idx.release(); table.i0.release(); table.w.release(); table.flag.release(); table.spans.release();
+        d_idx.release(); table.i0.release(); table.w.release(); table.flag.release();
     }
 };
 
@@ -115,6 +114,8 @@ struct dind_interp_s {
     DevBuf w_owned;
     DevBuf uw;          // u pre-multiplied by the weights
     bool uw_valid = false;
+    DevBuf u_aos;       // component-fastest copy of u (vector-valued unstructured evaluation)
+    bool u_aos_valid = false;
     // cell-sorted plan for eval_unstructured (dind_plan.cu)
     bool plan_valid = false;
     int64_t plan_n = 0;
@@ -217,8 +218,6 @@ DimParams<T> make_dim_params(const dind_interp_s* h, const DimState& D, int dim,
     P.width = D.width;
     P.n_u = (int32_t)D.n_u;
     P.order = order;
-    P.group_span2 = D.table.order >= 0 ? D.table.span2 : -1;
-    P.group_span4 = D.table.order >= 0 ? D.table.span4 : -1;
     return P;
 }
 
@@ -256,17 +255,6 @@ int ensure_table(dind_interp_s* h, int dim, int order) {
     DimParams<T> P = make_dim_params<T>(h, D, dim, order);
     CUDA_TRY(launch_axis_table<T>(P, order, (int32_t*)D.table.i0.p, (T*)D.table.w.p, (uint8_t*)D.table.flag.p, h->stream));
     h->launches += D.n_eval ? 1 : 0;
-    // how far the first stencil node moves inside aligned groups of 2 / 4 grid coordinates
-    // (tells the grid dispatcher whether the shared-row tile kernel applies); one 8-byte read-back
-    // per table build, i.e. per (t_eval, derivative order), never per evaluation
-    CUDA_TRY(D.table.spans.ensure(2 * sizeof(int32_t)));
-    CUDA_TRY(launch_group_span((const int32_t*)D.table.i0.p, D.n_eval, (int32_t*)D.table.spans.p, h->stream));
-    h->launches += D.n_eval ? 1 : 0;
-    int32_t sp[2] = {0, 0};
-    CUDA_TRY(cudaMemcpyAsync(sp, D.table.spans.p, sizeof sp, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    D.table.span2 = sp[0];
-    D.table.span4 = sp[1];
     D.table.order = order;
     return DIND_OK;
 }
@@ -416,7 +404,19 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     cudaError_t err = cudaSuccess;
     const char* name = nullptr;
     int nlaunch = 0;
-    if (!(flags & DIND_FLAG_GENERIC) && !const_deriv && !zero_result) {
+    const bool fast_ok = !(flags & DIND_FLAG_GENERIC) && !const_deriv && !zero_result;
+    if (fast_ok && !grid && aos_supported<T>(P) && !getenv("DIND_NO_AOS")) {
+        // vector-valued u: gather from the component-fastest copy (rebuilt once per dind_set_u)
+        if (!h->u_aos_valid) {
+            CUDA_TRY(h->u_aos.ensure((size_t)h->comp_stride * h->n_comp * sizeof(T)));
+            CUDA_TRY(launch_aos_repack<T>((const T*)h->d_u, (T*)h->u_aos.p, h->comp_stride, (int)h->n_comp, h->stream));
+            h->launches += 1;
+            h->u_aos_valid = true;
+        }
+        P.u_aos = (const T*)h->u_aos.p;
+        handled = try_eval_fast_unstructured_aos<T>(P, h->stream, &name, &err, &nlaunch);
+    }
+    if (fast_ok && !handled) {
         handled = grid ? try_eval_fast_grid<T>(P, h->stream, &name, &err, &nlaunch)
                        : try_eval_fast_unstructured<T>(P, h->stream, &name, &err, &nlaunch);
     }
@@ -532,7 +532,7 @@ int dind_destroy(dind_handle_t h) {
         h->dims[d].release();
         h->pts_stage[d].release();
     }
-    h->u_owned.release(); h->w_owned.release(); h->uw.release(); h->out_stage.release();
+    h->u_owned.release(); h->w_owned.release(); h->uw.release(); h->u_aos.release(); h->out_stage.release();
     h->plan_perm.release();
     for (int d = 0; d < MAXN; ++d) h->plan_t[d].release();
     delete h;
@@ -685,6 +685,7 @@ int dind_set_u(dind_handle_t h, const void* u, const int64_t* dims, int ndims, u
     h->n_comp = n_comp;
     h->u_set = true;
     h->uw_valid = false;
+    h->u_aos_valid = false;
     return DIND_OK;
 }
 

@@ -120,8 +120,6 @@ struct DimParams {
     const int32_t* lut;
     T lut_t0, lut_scale;
     int32_t lut_n;
-    int32_t group_span2;   // grid tables: max over aligned groups of 2 / 4 grid coordinates of
-    int32_t group_span4;   //   (max i0 - min i0); -1 = unknown
 };
 
 template <typename T>
@@ -129,6 +127,7 @@ struct EvalParams {
     DimParams<T> dim[MAXN];
     const T* u;            // (n_1..n_N, comps): NURBS: pre-multiplied by the weights
     const T* wts;          // NURBS weights (n_1..n_N) or null
+    const T* u_aos;        // optional component-fastest copy of u: u_aos[c + n_comp * i] (unstructured, 2..4 components)
     T* out;                // (n_points, comps)
     int64_t n_points;
     int64_t u_comp_stride;

@@ -1,0 +1,182 @@
+// dind_fast_unstructured_aos.cu — eval_unstructured! for vector-valued u (2..4 output components)
+// over a component-fastest ("AoS") copy of u.
+//
+// The reference stores u as (n_1..n_N, out...): every output component is a separate N-D volume,
+// so a C-component stencil gather touches C distant sectors per node (config 5: 32 corners x 4
+// components = 128 scattered 4-byte loads, ~6 KB of HBM traffic per iid point with 64-byte
+// fetches).  The handle keeps a repacked copy u_aos[c + C*i] (one extra pass per dind_set_u, SURVEY.md
+// §7.2 "repack allowed"): all components of a node are one 8/16-byte vector load, two nodes
+// adjacent along axis 1 share a 32-byte sector.  Outputs keep the reference's layout (n_points, out...).
+#include "dind_kernels.h"
+
+namespace dind {
+
+namespace {
+
+constexpr int ABLOCK = 256;
+
+template <typename T, int C>
+struct Vec {
+    T v[C];
+};
+
+// all components of one node: one vector load when the vector is 8 or 16 bytes
+template <typename T, int C>
+__device__ __forceinline__ Vec<T, C> load_node(const T* __restrict__ p) {
+    Vec<T, C> r;
+    if constexpr (sizeof(T) * C == 16) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+        memcpy(&r, &q, 16);
+    } else if constexpr (sizeof(T) * C == 8) {
+        const float2 q = __ldg(reinterpret_cast<const float2*>(p));
+        memcpy(&r, &q, 8);
+    } else if constexpr (sizeof(T) * C == 32) {
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(p));
+        const float4 q1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        memcpy(&r.v[0], &q0, 16);
+        memcpy(&r.v[C / 2], &q1, 16);
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) r.v[c] = __ldg(p + c);
+    }
+    return r;
+}
+
+template <typename T, int D, int W, int C>
+struct ContractV {
+    static __device__ __forceinline__ Vec<T, C> run(const T* __restrict__ p, const T (&w)[MAXN][W], const int (&stride)[MAXN]) {
+        Vec<T, C> acc;
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc.v[c] = T(0);
+#pragma unroll
+        for (int a = 0; a < W; ++a) {
+            const Vec<T, C> t = ContractV<T, D - 1, W, C>::run(p + a * stride[D], w, stride);
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc.v[c] = fma(w[D][a], t.v[c], acc.v[c]);
+        }
+        return acc;
+    }
+};
+template <typename T, int W, int C>
+struct ContractV<T, 0, W, C> {
+    static __device__ __forceinline__ Vec<T, C> run(const T* __restrict__ p, const T (&w)[MAXN][W], const int (&)[MAXN]) {
+        Vec<T, C> acc;
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc.v[c] = T(0);
+#pragma unroll
+        for (int a = 0; a < W; ++a) {
+            const Vec<T, C> t = load_node<T, C>(p + a * C);
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc.v[c] = fma(w[0][a], t.v[c], acc.v[c]);
+        }
+        return acc;
+    }
+};
+
+// same per-dimension stencil as dind_fast_unstructured.cu
+template <typename T, int W>
+__device__ __forceinline__ int stencil_ct(const DimParams<T>& D, T x, int cached_idx, T (&w)[W]) {
+    using K = typename KeyOf<T>::type;
+    const K kx = to_key(x);
+    const int n = D.n_knots;
+    if (W == 2 && D.kind == LINEAR) {
+        const int idx = cached_idx ? cached_idx : clampi(dim_count<T, false>(D, x, kx), 1, n - 1);
+        const int c = idx - 1;
+        const T t1 = __ldg(D.knots + c), t2 = __ldg(D.knots + c + 1), r = __ldg(D.recip + c);
+        if (D.order == 0) { w[0] = (t2 - x) * r; w[1] = (x - t1) * r; }
+        else { w[0] = -r; w[1] = r; }
+        return c;
+    }
+    const int idx = cached_idx ? cached_idx : clampi(dim_count<T, true>(D, x, kx), W, n - W);
+    bspline_basis_ct<T, W - 1>(D.knots, D.recip, n, idx - 1, x, D.order, w);
+    return idx - W;
+}
+
+template <typename T, int N, int W, int C>
+__global__ void __launch_bounds__(ABLOCK) unstructured_aos_kernel(const __grid_constant__ EvalParams<T> P) {
+    const int64_t k = (int64_t)blockIdx.x * ABLOCK + threadIdx.x;
+    if (k >= P.n_points) return;
+    T w[MAXN][W];
+    int stride[MAXN];
+    int64_t base = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const DimParams<T>& D = P.dim[d];
+        const T x = __ldcs(D.t_eval + k);
+        const int cached = P.use_cached_idx ? __ldcs(D.idx_eval + k) : 0;
+        const int i0 = stencil_ct<T, W>(D, x, cached, w[d]);
+        stride[d] = (int)D.u_stride * C;
+        base += (int64_t)i0 * D.u_stride;
+    }
+    const int64_t ko = P.perm ? (int64_t)__ldcs(P.perm + k) : k;
+    const Vec<T, C> acc = ContractV<T, N - 1, W, C>::run(P.u_aos + base * C, w, stride);
+#pragma unroll
+    for (int c = 0; c < C; ++c) __stcs(P.out + (int64_t)c * P.out_comp_stride + ko, acc.v[c]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ABLOCK) aos_repack_kernel(const T* __restrict__ u, T* __restrict__ u_aos, int64_t n, int C) {
+    const int64_t i = (int64_t)blockIdx.x * ABLOCK + threadIdx.x;
+    if (i >= n) return;
+    for (int c = 0; c < C; ++c) u_aos[i * C + c] = __ldcs(u + i + (int64_t)c * n);
+}
+
+template <typename T, int N, int W>
+cudaError_t launch_aos(const EvalParams<T>& P, cudaStream_t s) {
+    const unsigned nb = (unsigned)((P.n_points + ABLOCK - 1) / ABLOCK);
+    switch (P.n_comp) {
+        case 2: unstructured_aos_kernel<T, N, W, 2><<<nb, ABLOCK, 0, s>>>(P); break;
+        case 3: unstructured_aos_kernel<T, N, W, 3><<<nb, ABLOCK, 0, s>>>(P); break;
+        case 4: unstructured_aos_kernel<T, N, W, 4><<<nb, ABLOCK, 0, s>>>(P); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+template <typename T>
+cudaError_t launch_aos_repack(const T* u, T* u_aos, int64_t n, int n_comp, cudaStream_t s) {
+    aos_repack_kernel<T><<<(unsigned)((n + ABLOCK - 1) / ABLOCK), ABLOCK, 0, s>>>(u, u_aos, n, n_comp);
+    return cudaGetLastError();
+}
+
+template <typename T>
+bool aos_supported(const EvalParams<T>& P) {
+    const int N = P.n_in;
+    if (P.wts || P.n_comp < 2 || P.n_comp > 4 || N < 1 || N > 6) return false;
+    const int W = P.dim[0].width;
+    for (int d = 0; d < N; ++d) {
+        if (P.dim[d].width != W || P.dim[d].kind == CONSTANT) return false;
+        if (P.dim[d].kind == BSPLINE && P.dim[d].degree != W - 1) return false;
+    }
+    if (P.u_comp_stride * P.n_comp >= (1LL << 31)) return false;
+    if (W == 2) return true;
+    return (W == 3 || W == 4) && (N == 2 || N == 3);
+}
+
+template <typename T>
+bool try_eval_fast_unstructured_aos(const EvalParams<T>& P, cudaStream_t s, const char** name, cudaError_t* err, int* launches) {
+    if (!P.u_aos || !aos_supported(P)) return false;
+    const int N = P.n_in, W = P.dim[0].width;
+    *launches = 1;
+#define DIND_AOS(NN, WW)                                       \
+    if (N == NN && W == WW) {                                  \
+        *err = launch_aos<T, NN, WW>(P, s);                    \
+        *name = "unstructured_aos<N=" #NN ",W=" #WW ">";       \
+        return true;                                           \
+    }
+    DIND_AOS(1, 2) DIND_AOS(2, 2) DIND_AOS(3, 2) DIND_AOS(4, 2) DIND_AOS(5, 2) DIND_AOS(6, 2)
+    DIND_AOS(2, 3) DIND_AOS(3, 3) DIND_AOS(2, 4) DIND_AOS(3, 4)
+#undef DIND_AOS
+    return false;
+}
+
+#define DIND_INST(T)                                                                                              \
+    template cudaError_t launch_aos_repack<T>(const T*, T*, int64_t, int, cudaStream_t);                         \
+    template bool aos_supported<T>(const EvalParams<T>&);                                                         \
+    template bool try_eval_fast_unstructured_aos<T>(const EvalParams<T>&, cudaStream_t, const char**, cudaError_t*, int*);
+DIND_INST(float)
+DIND_INST(double)
+
+}  // namespace dind

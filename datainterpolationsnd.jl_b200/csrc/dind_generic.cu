@@ -68,17 +68,6 @@ __global__ void __launch_bounds__(BLOCK) lut_kernel(const T* __restrict__ knots,
     lut[b] = lo;
 }
 
-__global__ void __launch_bounds__(BLOCK) group_span_kernel(const int32_t* __restrict__ tab_i0, int64_t n, int32_t* __restrict__ spans) {
-    const int64_t q = ((int64_t)blockIdx.x * BLOCK + threadIdx.x) * 4;
-    if (q >= n) return;
-    int v[4];
-    for (int j = 0; j < 4; ++j) v[j] = tab_i0[q + j < n ? q + j : n - 1];
-    const int s2 = max(abs(v[1] - v[0]), abs(v[3] - v[2]));
-    const int s4 = max(max(v[0], v[1]), max(v[2], v[3])) - min(min(v[0], v[1]), min(v[2], v[3]));
-    if (s2 > 0) atomicMax(spans + 0, s2);
-    if (s4 > 0) atomicMax(spans + 1, s4);
-}
-
 template <typename T>
 __global__ void __launch_bounds__(BLOCK) premultiply_kernel(const T* __restrict__ u, const T* __restrict__ w,
                                                             T* __restrict__ uw, int64_t n, int n_comp) {
@@ -195,13 +184,6 @@ cudaError_t launch_axis_table(const DimParams<T>& D, int order, int32_t* tab_i0,
 template <typename T>
 cudaError_t launch_lut(const T* knots, int n_knots, T t0, T scale, int n_buckets, int32_t* lut, cudaStream_t s) {
     lut_kernel<T><<<blocks_for(n_buckets + 1, BLOCK), BLOCK, 0, s>>>(knots, n_knots, t0, scale, n_buckets, lut);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_group_span(const int32_t* tab_i0, int64_t n, int32_t* spans, cudaStream_t s) {
-    cudaError_t e = cudaMemsetAsync(spans, 0, 2 * sizeof(int32_t), s);
-    if (e != cudaSuccess || n == 0) return e;
-    group_span_kernel<<<blocks_for((n + 3) / 4, BLOCK), BLOCK, 0, s>>>(tab_i0, n, spans);
     return cudaGetLastError();
 }
 

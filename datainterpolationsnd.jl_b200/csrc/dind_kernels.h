@@ -14,8 +14,6 @@ template <typename T> cudaError_t launch_axis_table(const DimParams<T>& D, int o
                                                     uint8_t* tab_flag, cudaStream_t s);
 // bucket table of the interval search: lut[b] = #{i : lut_bucket(knots[i]) < b}, b = 0..n_buckets
 template <typename T> cudaError_t launch_lut(const T* knots, int n_knots, T t0, T scale, int n_buckets, int32_t* lut, cudaStream_t s);
-// spans[0] / spans[1] = max over aligned groups of 2 / 4 grid coordinates of (max i0 - min i0)
-cudaError_t launch_group_span(const int32_t* tab_i0, int64_t n, int32_t* spans, cudaStream_t s);
 // uw[i + c*n] = u[i + c*n] * w[i]  (NURBS numerator, src/interpolation_methods.jl:124-131)
 template <typename T> cudaError_t launch_premultiply(const T* u, const T* w, T* uw, int64_t n, int n_comp, cudaStream_t s);
 // generic evaluation: any N_in <= MAXN, any kinds, any degree <= MAXW-1
@@ -28,6 +26,12 @@ template <typename T> cudaError_t launch_eval_generic(const EvalParams<T>& P, bo
 template <typename T>
 cudaError_t plan_sort_points(const EvalParams<T>& P, uint32_t* perm, T* const* t_sorted, void* scratch,
                              size_t* scratch_bytes, cudaStream_t s);
+
+// Component-fastest repack of u for vector-valued unstructured evaluation (dind_fast_unstructured_aos.cu).
+template <typename T> cudaError_t launch_aos_repack(const T* u, T* u_aos, int64_t n, int n_comp, cudaStream_t s);
+template <typename T> bool aos_supported(const EvalParams<T>& P);
+template <typename T> bool try_eval_fast_unstructured_aos(const EvalParams<T>& P, cudaStream_t s, const char** name,
+                                                          cudaError_t* err, int* launches);
 
 // Specialised kernels.  Return true when they handled the evaluation (err holds the launch
 // status), false when the configuration is outside their envelope.
