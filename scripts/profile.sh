@@ -11,5 +11,5 @@ mkdir -p gpurun_out
 $CMD > gpurun_out/plain_$WL.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$WL.log; exit 1; }
 tail -1 gpurun_out/plain_$WL.log | cut -c1-300
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$WL.csv $CMD > gpurun_out/ncu_list_$WL.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"$RE" -s 3 -c 3 -f -o gpurun_out/${WL}_full $CMD > gpurun_out/ncu_full_$WL.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"$RE" -s 3 -c 1 -f -o gpurun_out/${WL}_full $CMD > gpurun_out/ncu_full_$WL.log 2>&1
 tail -2 gpurun_out/ncu_full_$WL.log | cut -c1-200
