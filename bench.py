@@ -124,10 +124,9 @@ class C4(Grid):
 
 class C4b(C4):
     """Variant with mixed kinds (no reference semantics): axis 3 is Constant(left=true)."""
-    name = "c4b: 4-D NURBS-weighted, axes (BSpline2, BSpline2, Constant(left=true), BSpline2) u=64^4 Float64 -> 128^4"
+    name = "c4b: 4-D NURBS (NURBSWeights), mixed axes (BSpline2, BSpline2, Constant(left=true), BSpline2) u=64^4 Float64 -> 128^4"
     key = "c4b"
     kinds, degrees = ("bspline", "bspline", "constant", "bspline"), (2, 2, 0, 2)
-    nurbs = False   # NURBS weights need all-BSpline dimensions (as in the reference's validate_cache)
 
 
 class Unstructured(Workload):

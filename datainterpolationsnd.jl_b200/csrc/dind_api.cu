@@ -271,10 +271,13 @@ int validate_interp(dind_interp_s* h) {
                             ? "Expected size(u, %d) == %lld based on the BSplineInterpolation properties, got %lld."
                             : "For the first N_in dimensions of u the length must match the t of the corresponding interpolation dimension (dim %d: expected %lld, got %lld).",
                         d + 1, (long long)h->dims[d].n_u, (long long)h->u_dims[d]);
+    // NURBS weights with Constant dimensions mixed in are an extension (no reference semantics: the
+    // weights multiply the tensor-product stencil weights); Linear dimensions are rejected — the
+    // reference would log an @error and silently ignore the weights (interpolation_utils.jl:65-67).
     if (h->w_set)
         for (int d = 0; d < h->n_in; ++d)
-            if (h->dims[d].kind != BSPLINE)
-                return fail(DIND_ERR_INVALID_ARGUMENT, "NURBS weights need BSpline interpolation dimensions (dimension %d is not)", d + 1);
+            if (h->dims[d].kind == LINEAR)
+                return fail(DIND_ERR_INVALID_ARGUMENT, "NURBS weights need BSpline interpolation dimensions (dimension %d is Linear)", d + 1);
     return DIND_OK;
 }
 
@@ -333,6 +336,8 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         P.dim[d] = make_dim_params<T>(h, D, d, orders[d]);
         P.dim[d].t_eval = (const T*)t_dev[d];
         P.dim[d].n_eval = n_eval[d];
+        P.dim[d].out_stride = 1;
+        if (grid) for (int e = 0; e < d; ++e) P.dim[d].out_stride *= n_eval[e];
         if (!have_idx_cache) P.dim[d].idx_eval = nullptr;
         if (D.kind == CONSTANT && orders[d] > 0) const_deriv = true;
         if (D.kind == LINEAR && orders[d] > 1) zero_result = true;

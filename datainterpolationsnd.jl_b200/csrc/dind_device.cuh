@@ -109,6 +109,7 @@ struct DimParams {
     const uint8_t* tab_flag;  // bit0: Constant-with-derivative on a knot
     int64_t n_eval;
     int64_t u_stride;      // element stride of this dimension in u
+    int64_t out_stride;    // grid evaluation: element stride of this axis in out
     int32_t n_knots;
     int32_t kind;
     int32_t degree;

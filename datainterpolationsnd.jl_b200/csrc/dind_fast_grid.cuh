@@ -309,7 +309,6 @@ __global__ void __launch_bounds__(PBLOCK, PF ? 5 : 8) grid_pencil_kernel(const _
         for (int a = 0; a < W; ++a) C.w1[v][a] = __ldg(P.dim[0].tab_w + g1c * W + a);
     }
     int64_t out_off = g1base;
-    int64_t mul = n1;
     int base = 0;
     int rel = 0;
     C.row0 = 0;
@@ -320,8 +319,7 @@ __global__ void __launch_bounds__(PBLOCK, PF ? 5 : 8) grid_pencil_kernel(const _
         const int rest = q / n2g;
         const int g2 = (q - rest * n2g) * J;
         q = rest;
-        out_off += mul * g2;
-        mul *= n2;
+        out_off += P.dim[1].out_stride * g2;
         int i02[J];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
@@ -350,9 +348,18 @@ __global__ void __launch_bounds__(PBLOCK, PF ? 5 : 8) grid_pencil_kernel(const _
             const int qq = q / ne;
             gm[d - 2] = q - qq * ne;
             q = qq;
-            out_off += mul * gm[d - 2];
-            mul *= ne;
+            out_off += P.dim[d].out_stride * gm[d - 2];
             base += __ldg(P.dim[d].tab_i0 + gm[d - 2]) * (int)P.dim[d].u_stride;
+        }
+        // "point" axes (stencil width 1, e.g. Constant dimensions between BSpline ones): they sit after
+        // the N stencil axes in P.dim (the host permutes them there) and only select a slice of u
+        for (int e = N; e < P.n_in; ++e) {
+            const int ne = (int)P.dim[e].n_eval;
+            const int qq = q / ne;
+            const int g = q - qq * ne;
+            q = qq;
+            out_off += P.dim[e].out_stride * g;
+            base += __ldg(P.dim[e].tab_i0 + g) * (int)P.dim[e].u_stride;
         }
 #pragma unroll
         for (int m = 0; m < Ctx::MID; ++m) {
@@ -369,9 +376,9 @@ __global__ void __launch_bounds__(PBLOCK, PF ? 5 : 8) grid_pencil_kernel(const _
 #pragma unroll
     for (int v = 0; v < VX; ++v) C.off1[v] += base;
     C.sN = (int)L.u_stride;
-    const int64_t R = mul;                       // points per last-axis coordinate
+    const int64_t R = L.out_stride;              // points per last-axis coordinate
     out_off += (int64_t)g_lo * R;
-    const int64_t jstride = n1;
+    const int64_t jstride = (N >= 3) ? P.dim[1].out_stride : 0;
 
     if (J == 1 || N < 3) walk_pencil<T, N, W, VX, J, NURBS, 0, FULL, PF>(P, C, s_i0, s_w, s_run, n_runs, R, out_off, jstride, ok);
     else if (rel == 0) walk_pencil<T, N, W, VX, J, NURBS, 0, FULL, PF>(P, C, s_i0, s_w, s_run, n_runs, R, out_off, jstride, ok);
@@ -386,6 +393,7 @@ cudaError_t launch_pencil_cfg(const EvalParams<T>& P, cudaStream_t s) {
     const int n2g = (N >= 3) ? ((int)P.dim[1].n_eval + J - 1) / J : 1;
     int64_t items = (int64_t)nseg * n2g;
     for (int d = 2; d < N - 1; ++d) items *= P.dim[d].n_eval;
+    for (int e = N; e < P.n_in; ++e) items *= P.dim[e].n_eval;
     const int n_last = (int)P.dim[N - 1].n_eval;
     const int bx = (int)((items + PWARPS - 1) / PWARPS);
     // >= ~6 waves of CTAs (short tail) while keeping pencils long enough to amortise the window start-up
@@ -432,24 +440,38 @@ cudaError_t launch_pencil(const EvalParams<T>& P, cudaStream_t s) {
 // Dispatch for NLO <= N_in <= NHI (the instantiations are spread over several translation
 // units to keep the build parallel).
 template <typename T, int NLO, int NHI>
-bool try_grid_range(const EvalParams<T>& P, cudaStream_t s, const char** name, cudaError_t* err, int* launches) {
-    const int N = P.n_in;
+bool try_grid_range(const EvalParams<T>& P0, cudaStream_t s, const char** name, cudaError_t* err, int* launches) {
+    const int NT = P0.n_in;
+    if (NT < 2) return false;
+    // Stencil axes (width W) keep their order in front; axes of width 1 (Constant) that lie strictly
+    // between axis 2 and the last axis become "point" axes behind them.
+    int W = 1;
+    for (int d = 0; d < NT; ++d) W = max(W, P0.dim[d].width);
+    if (W < 2 || W > 4) return false;
+    EvalParams<T> P = P0;
+    int ns = 0, np = 0;
+    int point[MAXN];
+    for (int d = 0; d < NT; ++d) {
+        if (P0.dim[d].width == W) P.dim[ns++] = P0.dim[d];
+        else if (P0.dim[d].width == 1 && d >= 2 && d < NT - 1) point[np++] = d;
+        else return false;
+    }
+    if (P0.dim[0].width != W || P0.dim[NT - 1].width != W || (ns >= 3 && P0.dim[1].width != W)) return false;
+    for (int e = 0; e < np; ++e) P.dim[ns + e] = P0.dim[point[e]];
+    const int N = ns;
     if (N < NLO || N > NHI || N < 2 || N > 5) return false;
-    const int W = P.dim[0].width;
     int64_t total = 1;
-    for (int d = 0; d < N; ++d) {
-        if (P.dim[d].width != W) return false;
+    for (int d = 0; d < NT; ++d) {
         if (P.dim[d].n_eval >= (1 << 30)) return false;
         total *= P.dim[d].n_eval;
     }
-    if (W < 2 || W > 4) return false;
     if (P.u_comp_stride >= (1LL << 31)) return false;
     if (total / P.dim[N - 1].n_eval >= (1LL << 31) || P.dim[N - 1].n_eval >= 65535) return false;
     *launches = 1;
 #define DIND_PENCIL(NN, WW)                                           \
     if (NN >= NLO && NN <= NHI && N == NN && W == WW) {               \
         *err = launch_pencil<T, (NN >= NLO && NN <= NHI) ? NN : NLO, WW>(P, s); \
-        *name = "grid_pencil<N=" #NN ",W=" #WW ">";                   \
+        *name = np ? "grid_pencil<N=" #NN "+point axes,W=" #WW ">" : "grid_pencil<N=" #NN ",W=" #WW ">"; \
         return true;                                                  \
     }
     DIND_PENCIL(2, 2) DIND_PENCIL(2, 3) DIND_PENCIL(2, 4)

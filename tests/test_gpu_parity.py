@@ -100,6 +100,8 @@ CASES = [
     (("bspline", "constant", "bspline"), (2, 0, 3), (6, 5, 6), (), [(0, 0, 0), (1, 0, 0)]),
     (("linear", "bspline"), (0, 2), (6, 5), (2,), [(0, 0), (1, 1)]),
     (("constant", "linear", "bspline"), (0, 0, 1), (4, 5, 6), (), [(0, 0, 0), (0, 1, 0)]),
+    (("bspline", "bspline", "constant", "bspline"), (2, 2, 0, 2), (5, 4, 5, 4), (), [(0, 0, 0, 0), (1, 0, 0, 0)]),
+    (("linear", "linear", "constant", "constant", "linear"), (0,) * 5, (4, 3, 4, 3, 4), (2,), [(0,) * 5]),
 ]
 
 
@@ -412,3 +414,23 @@ def test_cell_sorted_plan_is_bit_identical(D, dtype, case):
     b = D.eval_unstructured(itp, flags=CELL_SORTED)
     assert np.array_equal(a, b, equal_nan=True)
     itp.close()
+
+
+def test_nurbs_weights_with_constant_axis(D):
+    """BASELINE config 4 names NURBS weights with mixed Constant(left=true)/BSpline dimensions: no
+    reference semantics — defined as the tensor product of the per-dimension stencils
+    with the weights multiplied in, checked against the oracle's mixed evaluator and by slice
+    equivalence against the all-BSpline NURBS evaluation of the selected slice."""
+    rng = np.random.default_rng(77)
+    kinds, degrees = ("bspline", "bspline", "constant", "bspline"), (2, 2, 0, 2)
+    ts, u, w = _case(rng, kinds, degrees, (6, 5, 5, 6), (), np.float64, nurbs=True)
+    xg = [np.sort(H.query(rng, t, 9, np.float64, outside=False)) for t in ts]
+    ref = H.oracle_eval(kinds, ts, u, xg, degrees=degrees, weights=w, grid=True)
+    for flags in (0, GENERIC):
+        got, kern = H.gpu_eval(D, kinds, ts, u, xg, degrees=degrees, weights=w, grid=True, flags=flags)
+        H.assert_close(got, ref, np.float64, factor=8.0)
+    j = np.where(xg[2] >= ts[2][-1], len(ts[2]), O.get_idx("constant", ts[2], xg[2])) - 1
+    for k in (0, len(xg[2]) // 2, len(xg[2]) - 1):
+        sl = H.oracle_eval(("bspline",) * 3, [ts[0], ts[1], ts[3]], u[:, :, j[k], :], [xg[0], xg[1], xg[3]],
+                           degrees=(2, 2, 2), weights=w[:, :, j[k], :], grid=True)
+        H.assert_close(got[:, :, k, :], sl, np.float64, factor=8.0)
