@@ -283,9 +283,19 @@ def run_gpu(args, wl, rank, world, local_rank):
         out = D.f_empty((n,) + shape[len(wl.kinds):], wl.dtype, dev)
 
         uflags = 1 | (16 if args.sorted else 0)   # DIND_FLAG_ASYNC | DIND_FLAG_CELL_SORTED
+        n_in = len(wl.kinds)
+        if args.gradient:
+            gout = D.f_empty((n,) + shape[n_in:] + (n_in + 1,), wl.dtype, dev)
+            unit = [tuple(1 if d + 1 == s else 0 for d in range(n_in)) for s in range(n_in + 1)]
 
         def step(i):
-            D.eval_unstructured_(out, itp, flags=uflags)
+            if args.gradient == "fused":        # value + all first partials in one pass
+                D.eval_unstructured_gradient(itp, gout, flags=uflags)
+            elif args.gradient == "separate":   # what the reference needs: N_in + 1 eval_unstructured! calls
+                for s_ in range(n_in + 1):
+                    D.eval_unstructured_(gout[..., s_], itp, derivative_orders=unit[s_], flags=uflags)
+            else:
+                D.eval_unstructured_(out, itp, flags=uflags)
 
     def barrier():
         if world > 1:
@@ -367,7 +377,7 @@ def run_gpu(args, wl, rank, world, local_rank):
         "config": {"workload": wl.name, "points_per_step_per_gpu": wl.points_per_step(),
                    "sharding": ("slab along the last grid axis" if wl.grid else "contiguous index range") + ", u/knots replicated, no collective",
                    "l2": f"working set exceeds L2 (126 MB): output streamed, u rotates over {wl.n_u_buffers} buffers" if wl.grid else "t_eval + out exceed L2",
-                   "kernel": kernel, "point_order": ("iid random, evaluated through the cell-sorted plan" if args.sorted else "iid random") if not wl.grid else "grid"},
+                   "kernel": kernel, "gradient": args.gradient, "point_order": ("iid random, evaluated through the cell-sorted plan" if args.sorted else "iid random") if not wl.grid else "grid"},
         "e2e": {"value": round(pts_step_all / (e2e_ms * 1e-3) / 1e9, 4), "unit": "Gpoints/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "host (pinned) buffers through the public API; synchronous call incl. H2D + kernel + D2H"},
@@ -472,6 +482,8 @@ def main():
     ap.add_argument("--full", action="store_true", help="full-size point counts for c3 / c5")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink c2 (debugging only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gradient", choices=["fused", "separate"], default=None,
+                    help="unstructured workloads: a step evaluates value + all first partials (one fused pass, or N_in+1 calls)")
     ap.add_argument("--sorted", action="store_true", help="unstructured workloads: evaluate through the cell-sorted plan")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup

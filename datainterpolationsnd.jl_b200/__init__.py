@@ -33,7 +33,7 @@ __all__ = [
     "NDInterpolation", "LinearInterpolationDimension", "ConstantInterpolationDimension",
     "BSplineInterpolationDimension", "NURBSWeights", "EmptyCache", "eval_unstructured",
     "eval_unstructured_", "eval_grid", "eval_grid_", "DindError", "f_empty", "shard_range",
-    "shard_t_eval", "gather_unstructured", "gather_grid",
+    "shard_t_eval", "gather_unstructured", "gather_grid", "eval_unstructured_gradient",
 ]
 
 
@@ -408,6 +408,18 @@ def eval_unstructured_(out, interp, *, derivative_orders=None, flags=0):
     """eval_unstructured!(out, interp; derivative_orders) — src/interpolation_parallel.jl:34-52."""
     n_points = int(interp.interp_dims[0].t_eval.shape[0])
     return interp._eval(interp._h.lib.dind_eval_unstructured, out, (n_points,) + interp.output_size, derivative_orders, flags)
+
+
+def eval_unstructured_gradient(interp, out=None, *, flags=0):
+    """Value and all first partial derivatives at the cached unstructured points in one pass
+    (dind_eval_unstructured_gradient; beyond the reference, which needs N_in + 1 eval_unstructured calls).
+    Returns / fills an array of shape (n_points, out..., N_in + 1): [..., 0] = value, [..., d] = d/dt_d."""
+    n_points = int(interp.interp_dims[0].t_eval.shape[0])
+    shape = (n_points,) + interp.output_size + (interp.N_in + 1,)
+    out_arr = interp._make_out(shape) if out is None else out
+    res = interp._out_ptr(out_arr, shape)
+    _lib.check(interp._h.lib.dind_eval_unstructured_gradient(interp._h.h, C.c_void_p(res[0]), int(flags)))
+    return res[1]()
 
 
 def eval_grid(interp, *, derivative_orders=None, flags=0):

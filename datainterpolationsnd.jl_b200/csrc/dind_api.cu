@@ -314,7 +314,7 @@ int ensure_premultiplied(dind_interp_s* h) {
 // Common evaluation driver.  t_ptrs: device pointers to the per-dimension evaluation points.
 template <typename T>
 int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const void* const* t_dev,
-             const int64_t* n_eval, bool have_idx_cache, unsigned flags) {
+             const int64_t* n_eval, bool have_idx_cache, unsigned flags, bool gradient = false) {
     const int N = h->n_in;
     int64_t n_points = 1;
     if (grid) for (int d = 0; d < N; ++d) n_points *= n_eval[d];
@@ -345,7 +345,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     const bool out_on_device = is_device_ptr(out);
     if ((flags & DIND_FLAG_ASYNC) && !out_on_device)
         return fail(DIND_ERR_INVALID_ARGUMENT, "DIND_FLAG_ASYNC needs a device `out` pointer");
-    const size_t out_bytes = (size_t)n_points * h->n_comp * sizeof(T);
+    const size_t out_bytes = (size_t)n_points * h->n_comp * sizeof(T) * (gradient ? N + 1 : 1);
     T* d_out = (T*)out;
     const bool untouched_semantics = const_deriv && h->u_dims.size() > (size_t)N;
     if (!out_on_device) {
@@ -410,7 +410,26 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     const char* name = nullptr;
     int nlaunch = 0;
     const bool fast_ok = !(flags & DIND_FLAG_GENERIC) && !const_deriv && !zero_result;
-    if (fast_ok && !grid && aos_supported<T>(P) && !getenv("DIND_NO_AOS")) {
+    if (gradient) {
+        // one fused pass when the configuration is in the kernel's envelope, otherwise n_in + 1
+        // ordinary evaluations into the n_in + 1 output slots
+        if (fast_ok) handled = try_eval_fast_gradient<T>(P, h->stream, &name, &err, &nlaunch);
+        if (!handled) {
+            const int64_t slot = n_points * h->n_comp;
+            for (int sidx = 0; sidx <= N && err == cudaSuccess; ++sidx) {
+                EvalParams<T> Q = P;
+                for (int d = 0; d < N; ++d) Q.dim[d].order = (d + 1 == sidx) ? 1 : 0;
+                Q.out = d_out + sidx * slot;
+                int nl = 0;
+                bool ok = !(flags & DIND_FLAG_GENERIC) && try_eval_fast_unstructured<T>(Q, h->stream, &name, &err, &nl);
+                if (!ok) { err = launch_eval_generic<T>(Q, false, h->stream); nl = 1; }
+                nlaunch += nl;
+            }
+            name = "gradient_by_separate_evaluations";
+            handled = true;
+        }
+    }
+    if (!handled && fast_ok && !grid && aos_supported<T>(P) && !getenv("DIND_NO_AOS")) {
         // vector-valued u: gather from the component-fastest copy (rebuilt once per dind_set_u)
         if (!h->u_aos_valid) {
             CUDA_TRY(h->u_aos.ensure((size_t)h->comp_stride * h->n_comp * sizeof(T)));
@@ -739,6 +758,39 @@ int dind_eval_grid(dind_handle_t h, void* out, const int* derivative_orders, uns
     if (rc) return rc;
     return h->dtype == DIND_F32 ? eval_cached<float>(h, out, derivative_orders, true, flags)
                                 : eval_cached<double>(h, out, derivative_orders, true, flags);
+}
+
+extern "C++" {
+namespace {
+template <typename T>
+int eval_gradient(dind_interp_s* h, void* out, unsigned flags) {
+    int rc = validate_interp(h);
+    if (rc) return rc;
+    if (h->w_set) return fail(DIND_ERR_UNSUPPORTED, "Currently partial derivatives of NURBS are not supported.");
+    int orders[MAXN] = {0};
+    const void* t_dev[MAXN];
+    int64_t n_eval[MAXN];
+    for (int d = 0; d < h->n_in; ++d) {
+        const DimState& D = h->dims[d];
+        if (D.kind == CONSTANT) return fail(DIND_ERR_UNSUPPORTED, "dind_eval_unstructured_gradient does not take Constant dimensions");
+        if (D.kind == BSPLINE && D.max_deriv < 1)
+            return fail(DIND_ERR_INVALID_ARGUMENT, "BSpline dimension %d needs max_derivative_order_eval >= 1 for gradients", d + 1);
+        if (!D.teval_set) return fail(DIND_ERR_STATE, "t_eval of dimension %d has not been set (dind_set_t_eval)", d + 1);
+        t_dev[d] = D.d_teval;
+        n_eval[d] = D.n_eval;
+        if (n_eval[d] != h->dims[0].n_eval)
+            return fail(DIND_ERR_SIZE_MISMATCH, "The t_eval of all interpolation dimensions must have the same length as the first dimension of out.");
+    }
+    if (!out) return fail(DIND_ERR_INVALID_ARGUMENT, "out is NULL");
+    return run_eval<T>(h, out, orders, false, t_dev, n_eval, true, flags & ~DIND_FLAG_CACHED_IDX, true);
+}
+}  // namespace
+}  // extern "C++"
+
+int dind_eval_unstructured_gradient(dind_handle_t h, void* out, unsigned flags) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    return h->dtype == DIND_F32 ? eval_gradient<float>(h, out, flags) : eval_gradient<double>(h, out, flags);
 }
 
 int dind_eval_points(dind_handle_t h, void* out, const void* const* t, int64_t n, const int* derivative_orders,

@@ -33,6 +33,10 @@ template <typename T> bool aos_supported(const EvalParams<T>& P);
 template <typename T> bool try_eval_fast_unstructured_aos(const EvalParams<T>& P, cudaStream_t s, const char** name,
                                                           cudaError_t* err, int* launches);
 
+// Fused value + first partial derivatives (dind_fast_gradient.cu): out[(point, comp, slot)], slot 0 = value.
+template <typename T> bool try_eval_fast_gradient(const EvalParams<T>& P, cudaStream_t s, const char** name,
+                                                  cudaError_t* err, int* launches);
+
 // Specialised kernels.  Return true when they handled the evaluation (err holds the launch
 // status), false when the configuration is outside their envelope.
 template <typename T> bool try_eval_fast_unstructured(const EvalParams<T>& P, cudaStream_t s, const char** name,

@@ -16,7 +16,7 @@ using Libdl
 
 export NDInterpolation, LinearInterpolationDimension, ConstantInterpolationDimension,
     BSplineInterpolationDimension, NURBSWeights, EmptyCache,
-    eval_unstructured, eval_unstructured!, eval_grid, eval_grid!
+    eval_unstructured, eval_unstructured!, eval_grid, eval_grid!, eval_unstructured_gradient!
 
 const libdind = Ref{String}(get(ENV, "LIBDIND", joinpath(@__DIR__, "..", "..", "..", "libdind.so")))
 
@@ -190,6 +190,20 @@ end
 function eval_grid(itp::NDInterpolation{N_in}; kwargs...) where {N_in}
     out = similar(itp.u, (map(d -> length(d.t_eval), itp.interp_dims)..., get_output_size(itp)...))
     return eval_grid!(out, itp; kwargs...)
+end
+
+# ---- beyond the reference: value + all first partial derivatives in one pass -----------------------------
+"""
+    eval_unstructured_gradient!(out, itp)
+
+`out[k, .., 1]` = value, `out[k, .., 1 + d]` = ∂/∂t_d at the cached unstructured points; equivalent to
+`N_in + 1` calls of `eval_unstructured!` with unit `derivative_orders`, in one kernel pass.
+"""
+function eval_unstructured_gradient!(out::AbstractArray{T}, itp::NDInterpolation{N_in, N_out, T}) where {N_in, N_out, T}
+    @assert size(out) == (length(first(itp.interp_dims).t_eval), get_output_size(itp)..., N_in + 1)
+    GC.@preserve out check(ccall((:dind_eval_unstructured_gradient, libdind[]), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cuint), itp.handle, out, 0))
+    return out
 end
 
 # ---- single point calls (src/DataInterpolationsND.jl:73-100) through dind_eval_points with n = 1 --------

@@ -135,6 +135,15 @@ int dind_eval_grid(dind_handle_t handle, void* out, const int* derivative_orders
 int dind_eval_points(dind_handle_t handle, void* out, const void* const* t, int64_t n,
                      const int* derivative_orders, unsigned flags);
 
+/* Beyond the reference: value and ALL first partial derivatives of the
+ * cached unstructured points in one pass — equivalent to n_in + 1 calls of dind_eval_unstructured
+ * with derivative_orders = (0..0), e_1, .., e_{n_in} (what the reference needs for a gradient,
+ * src/interpolation_parallel.jl:34-52), sharing the interval search, the basis and the gather of u.
+ * out: (n_points, out..., n_in + 1) column-major; slot 0 = value, slot d = d/dt_d.
+ * Linear and BSpline dimensions (BSpline needs max_derivative_order_eval >= 1); Constant dimensions
+ * and NURBS weights return DIND_ERR_UNSUPPORTED.  Honours DIND_FLAG_ASYNC / DIND_FLAG_CELL_SORTED. */
+int dind_eval_unstructured_gradient(dind_handle_t handle, void* out, unsigned flags);
+
 /* ---- introspection (parity tests; fields the reference exposes on its structs) ---------- */
 /* idx_eval, 1-based Int64 exactly as the reference stores it (src/interpolation_dimensions.jl:38). */
 int dind_get_idx_eval(dind_handle_t handle, int dim, int64_t* idx_out /* host, n_eval */);

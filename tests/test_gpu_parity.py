@@ -434,3 +434,37 @@ def test_nurbs_weights_with_constant_axis(D):
         sl = H.oracle_eval(("bspline",) * 3, [ts[0], ts[1], ts[3]], u[:, :, j[k], :], [xg[0], xg[1], xg[3]],
                            degrees=(2, 2, 2), weights=w[:, :, j[k], :], grid=True)
         H.assert_close(got[:, :, k, :], sl, np.float64, factor=8.0)
+
+
+# ---- fused value + gradient (beyond the reference: SURVEY.md §8f rank 1) ---------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("flags", [0, CELL_SORTED, GENERIC])
+@pytest.mark.parametrize("case", [1, 2, 3, 7, 9, 12])
+def test_fused_gradient_equals_separate_evaluations(D, dtype, flags, case):
+    kinds, degrees, n_knots, out_dims, _ = CASES[case]
+    rng = np.random.default_rng(500 + case)
+    ts, u, _ = _case(rng, kinds, degrees, n_knots, out_dims, dtype)
+    xs = H.zipped_queries(rng, ts, 4000, dtype)
+    n = len(kinds)
+    dims = H.make_dims(D, kinds, ts, xs, degrees, None, max_deriv=[1] * n)
+    itp = D.NDInterpolation(u, dims)
+    g = D.eval_unstructured_gradient(itp, flags=flags)
+    assert g.shape == (xs[0].size,) + tuple(out_dims) + (n + 1,)
+    for s in range(n + 1):
+        orders = tuple(1 if d + 1 == s else 0 for d in range(n))
+        ref = H.oracle_eval(kinds, ts, u, xs, degrees=degrees, derivative_orders=orders)
+        H.assert_close(g[..., s], ref, dtype, factor=4.0)
+    itp.close()
+
+
+def test_fused_gradient_rejects_constant_and_nurbs(D):
+    t = np.array([0.0, 1.0, 2.0, 3.0])
+    itp = D.NDInterpolation(np.zeros(4), D.ConstantInterpolationDimension(t, t_eval=[0.5]))
+    with pytest.raises(AssertionError):
+        D.eval_unstructured_gradient(itp)
+    itp.close()
+    bs = D.BSplineInterpolationDimension(t, 2, t_eval=[0.5], max_derivative_order_eval=1)
+    itp = D.NDInterpolation(np.zeros(5), bs, cache=D.NURBSWeights(np.ones(5)))
+    with pytest.raises(AssertionError):
+        D.eval_unstructured_gradient(itp)
+    itp.close()
