@@ -282,7 +282,7 @@ def run_gpu(args, wl, rank, world, local_rank):
         itp = D.NDInterpolation(ud, dims, device=local_rank, stream=stream.cuda_stream)
         out = D.f_empty((n,) + shape[len(wl.kinds):], wl.dtype, dev)
 
-        uflags = 1 | (16 if args.sorted else 0)   # DIND_FLAG_ASYNC | DIND_FLAG_CELL_SORTED
+        uflags = 1 | (16 if args.sorted else 0) | (32 if args.plan_order else 0)   # ASYNC | CELL_SORTED | PLAN_ORDER
         n_in = len(wl.kinds)
         if args.gradient:
             gout = D.f_empty((n,) + shape[n_in:] + (n_in + 1,), wl.dtype, dev)
@@ -377,7 +377,7 @@ def run_gpu(args, wl, rank, world, local_rank):
         "config": {"workload": wl.name, "points_per_step_per_gpu": wl.points_per_step(),
                    "sharding": ("slab along the last grid axis" if wl.grid else "contiguous index range") + ", u/knots replicated, no collective",
                    "l2": f"working set exceeds L2 (126 MB): output streamed, u rotates over {wl.n_u_buffers} buffers" if wl.grid else "t_eval + out exceed L2",
-                   "kernel": kernel, "gradient": args.gradient, "point_order": ("iid random, evaluated through the cell-sorted plan" if args.sorted else "iid random") if not wl.grid else "grid"},
+                   "kernel": kernel, "gradient": args.gradient, "point_order": ("iid random, evaluated through the cell-sorted plan" + (", output left in plan order" if args.plan_order else "") if args.sorted else "iid random") if not wl.grid else "grid"},
         "e2e": {"value": round(pts_step_all / (e2e_ms * 1e-3) / 1e9, 4), "unit": "Gpoints/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "host (pinned) buffers through the public API; synchronous call incl. H2D + kernel + D2H"},
@@ -484,6 +484,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gradient", choices=["fused", "separate"], default=None,
                     help="unstructured workloads: a step evaluates value + all first partials (one fused pass, or N_in+1 calls)")
+    ap.add_argument("--plan-order", action="store_true", help="with --sorted: leave the output in plan order (no scatter)")
     ap.add_argument("--sorted", action="store_true", help="unstructured workloads: evaluate through the cell-sorted plan")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup

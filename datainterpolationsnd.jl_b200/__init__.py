@@ -319,6 +319,13 @@ class NDInterpolation:
     def last_kernel(self):
         return self._h.lib.dind_last_kernel(self._h.h).decode()
 
+    def plan_permutation(self):
+        """perm (uint32, n_points) of the cell-sorted plan: plan position k holds original point perm[k]."""
+        n = int(self.interp_dims[0].t_eval.shape[0])
+        out = np.empty(n, dtype=np.uint32)
+        _lib.check(self._h.lib.dind_get_plan_permutation(self._h.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     @property
     def launch_count(self):
         return int(self._h.lib.dind_launch_count(self._h.h))

@@ -12,6 +12,7 @@ ERR_INVALID_ARGUMENT, ERR_SIZE_MISMATCH, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE, E
 F32, F64 = 0, 1
 LINEAR, CONSTANT, BSPLINE = 0, 1, 2
 FLAG_ASYNC, FLAG_COPY, FLAG_CACHED_IDX, FLAG_GENERIC, FLAG_CELL_SORTED = 1, 2, 4, 8, 16
+FLAG_PLAN_ORDER = 32
 MAX_DIMS, MAX_DEGREE = 8, 7
 
 # every symbol include/dind.h declares: (name, restype, argtypes)
@@ -33,6 +34,7 @@ SYMBOLS = [
     ("dind_get_idx_eval", _i, [_vp, _i, _pi64]),
     ("dind_get_knots_all", _i, [_vp, _i, _vp, _pi64]),
     ("dind_get_basis_function_eval", _i, [_vp, _i, _vp]),
+    ("dind_get_plan_permutation", _i, [_vp, _vp]),
     ("dind_last_kernel", C.c_char_p, [_vp]),
     ("dind_launch_count", _i64, [_vp]),
     ("dind_shard_range", _i, [_i64, _i, _i, _pi64, _pi64]),

@@ -119,7 +119,7 @@ struct dind_interp_s {
     // cell-sorted plan for eval_unstructured (dind_plan.cu)
     bool plan_valid = false;
     int64_t plan_n = 0;
-    DevBuf plan_perm;
+    DevBuf plan_perm, plan_inv, plan_stage;
     DevBuf plan_t[MAXN];
     // staging
     DevBuf out_stage;
@@ -361,6 +361,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     P.n_points = n_points;
     P.u_comp_stride = h->comp_stride;
     P.out_comp_stride = n_points;
+    P.out_point_stride = 1;
     P.n_comp = (int32_t)h->n_comp;
     P.n_in = N;
     P.scalar_out = h->u_dims.size() == (size_t)N;
@@ -375,6 +376,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         }
     }
 
+    int unperm_ct = 0;   // > 0: results are staged in plan order and gathered back after the kernel
     if (!grid && have_idx_cache && (flags & DIND_FLAG_CELL_SORTED)) {
         if (n_points >= (1LL << 32) || h->comp_stride >= (1LL << 32))
             return fail(DIND_ERR_UNSUPPORTED, "DIND_FLAG_CELL_SORTED needs fewer than 2^32 points and u elements per component");
@@ -393,7 +395,9 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
             if (pe == cudaSuccess) pe = cudaStreamSynchronize(h->stream);
             scratch.release();
             CUDA_TRY(pe);
-            h->launches += 2 + N;
+            CUDA_TRY(h->plan_inv.ensure((size_t)n_points * sizeof(uint32_t)));
+            CUDA_TRY(plan_inverse((const uint32_t*)h->plan_perm.p, (uint32_t*)h->plan_inv.p, n_points, h->stream));
+            h->launches += 3 + N;
             h->plan_valid = true;
             h->plan_n = n_points;
         }
@@ -402,7 +406,20 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
             P.dim[d].idx_eval = nullptr;
         }
         P.use_cached_idx = 0;
-        P.perm = (const uint32_t*)h->plan_perm.p;
+        P.perm = (flags & DIND_FLAG_PLAN_ORDER) ? nullptr : (const uint32_t*)h->plan_perm.p;
+        // Results go back to their original positions through a component-fastest staging buffer in
+        // plan order + one gather pass (one random read per point) — a direct scatter costs one random
+        // read-modify-write of a 32-byte sector per point AND component and bounds the whole path.
+        // (Constant-with-derivative keeps the direct scatter: it must leave entries untouched.)
+        if (P.perm && !const_deriv) {
+            const int ct = (int)h->n_comp * (gradient ? N + 1 : 1);
+            CUDA_TRY(h->plan_stage.ensure((size_t)n_points * ct * sizeof(T)));
+            unperm_ct = ct;
+            P.perm = nullptr;
+            P.out = (T*)h->plan_stage.p;
+            P.out_point_stride = ct;
+            P.out_comp_stride = 1;
+        }
     }
 
     bool handled = false;
@@ -415,11 +432,11 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         // ordinary evaluations into the n_in + 1 output slots
         if (fast_ok) handled = try_eval_fast_gradient<T>(P, h->stream, &name, &err, &nlaunch);
         if (!handled) {
-            const int64_t slot = n_points * h->n_comp;
+            const int64_t slot = P.out_comp_stride * h->n_comp;   // n_points * n_comp, or n_comp when staged in plan order
             for (int sidx = 0; sidx <= N && err == cudaSuccess; ++sidx) {
                 EvalParams<T> Q = P;
                 for (int d = 0; d < N; ++d) Q.dim[d].order = (d + 1 == sidx) ? 1 : 0;
-                Q.out = d_out + sidx * slot;
+                Q.out = P.out + sidx * slot;
                 int nl = 0;
                 bool ok = !(flags & DIND_FLAG_GENERIC) && try_eval_fast_unstructured<T>(Q, h->stream, &name, &err, &nl);
                 if (!ok) { err = launch_eval_generic<T>(Q, false, h->stream); nl = 1; }
@@ -452,6 +469,10 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     CUDA_TRY(err);
     h->last_kernel = name;
     h->launches += nlaunch;
+    if (unperm_ct) {
+        CUDA_TRY(plan_unpermute<T>((const T*)h->plan_stage.p, (const uint32_t*)h->plan_inv.p, d_out, n_points, unperm_ct, h->stream));
+        h->launches += 1;
+    }
     if (!out_on_device) {
         CUDA_TRY(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -557,7 +578,7 @@ int dind_destroy(dind_handle_t h) {
         h->pts_stage[d].release();
     }
     h->u_owned.release(); h->w_owned.release(); h->uw.release(); h->u_aos.release(); h->out_stage.release();
-    h->plan_perm.release();
+    h->plan_perm.release(); h->plan_inv.release(); h->plan_stage.release();
     for (int d = 0; d < MAXN; ++d) h->plan_t[d].release();
     delete h;
     return DIND_OK;
@@ -853,6 +874,17 @@ int dind_get_basis_function_eval(dind_handle_t h, int dim, void* basis_out) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     tmp.release();
     CUDA_TRY(e);
+    return DIND_OK;
+}
+
+int dind_get_plan_permutation(dind_handle_t h, uint32_t* perm_out) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!h->plan_valid) return fail(DIND_ERR_STATE, "no cell-sorted plan: evaluate with DIND_FLAG_CELL_SORTED first");
+    if (!perm_out) return fail(DIND_ERR_INVALID_ARGUMENT, "perm_out is NULL");
+    CUDA_TRY(cudaMemcpyAsync(perm_out, h->plan_perm.p, (size_t)h->plan_n * sizeof(uint32_t),
+                             is_device_ptr(perm_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     return DIND_OK;
 }
 

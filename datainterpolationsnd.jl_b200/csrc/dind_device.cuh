@@ -133,6 +133,7 @@ struct EvalParams {
     int64_t n_points;
     int64_t u_comp_stride;
     int64_t out_comp_stride;
+    int64_t out_point_stride;  // 1 for the reference layout (points fastest); n_comp for the plan's component-fastest staging
     int32_t n_comp;
     int32_t n_in;
     int32_t scalar_out;    // N_out == 0

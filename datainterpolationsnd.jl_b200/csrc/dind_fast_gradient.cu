@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(GBLOCK) unstructured_gradient_kernel(const __g
     const int64_t slot = P.out_comp_stride * P.n_comp;   // elements per (value | derivative) block
     for (int c = 0; c < P.n_comp; ++c) {
         const GVec<T, N + 1> g = ContractG<T, N - 1, W>::run(P.u + (int64_t)c * P.u_comp_stride + base, w, dw, stride);
-        T* o = P.out + (int64_t)c * P.out_comp_stride + ko;
+        T* o = P.out + (int64_t)c * P.out_comp_stride + ko * P.out_point_stride;
 #pragma unroll
         for (int j = 0; j < N + 1; ++j) __stcs(o + j * slot, g.g[j]);
     }

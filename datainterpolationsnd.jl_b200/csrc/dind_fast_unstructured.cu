@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(UBLOCK) unstructured_kernel(const __grid_const
     const int64_t ko = P.perm ? (int64_t)__ldcs(P.perm + k) : k;   // cell-sorted plan: scatter to the original position
     for (int c = 0; c < P.n_comp; ++c) {
         const T acc = ContractU<T, N - 1, W>::run(P.u + (int64_t)c * P.u_comp_stride + base, w, stride);
-        __stcs(P.out + (int64_t)c * P.out_comp_stride + ko, NURBS ? acc / den : acc);
+        __stcs(P.out + (int64_t)c * P.out_comp_stride + ko * P.out_point_stride, NURBS ? acc / den : acc);
     }
 }
 

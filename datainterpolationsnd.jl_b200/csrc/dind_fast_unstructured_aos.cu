@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(ABLOCK) unstructured_aos_kernel(const __grid_c
     const int64_t ko = P.perm ? (int64_t)__ldcs(P.perm + k) : k;
     const Vec<T, C> acc = ContractV<T, N - 1, W, C>::run(P.u_aos + base * C, w, stride);
 #pragma unroll
-    for (int c = 0; c < C; ++c) __stcs(P.out + (int64_t)c * P.out_comp_stride + ko, acc.v[c]);
+    for (int c = 0; c < C; ++c) __stcs(P.out + (int64_t)c * P.out_comp_stride + ko * P.out_point_stride, acc.v[c]);
 }
 
 template <typename T>

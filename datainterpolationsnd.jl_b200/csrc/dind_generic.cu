@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(BLOCK) eval_generic_kernel(const __grid_consta
     const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (k >= P.n_points) return;
     const int N = P.n_in;
-    const int64_t ko = (!GRID && P.perm) ? (int64_t)P.perm[k] : k;   // output position (cell-sorted plan)
+    const int64_t ko = ((!GRID && P.perm) ? (int64_t)P.perm[k] : k) * (GRID ? 1 : P.out_point_stride);   // output position (cell-sorted plan)
     int i0[MAXN];
     T w[MAXN][MAXW];
     bool any_on_knot = false;

@@ -37,6 +37,11 @@ template <typename T> bool try_eval_fast_unstructured_aos(const EvalParams<T>& P
 template <typename T> bool try_eval_fast_gradient(const EvalParams<T>& P, cudaStream_t s, const char** name,
                                                   cudaError_t* err, int* launches);
 
+// inv[perm[k]] = k, and the gather that brings plan-ordered, component-fastest staged results back to
+// the reference layout out[(point, component)].
+cudaError_t plan_inverse(const uint32_t* perm, uint32_t* inv, int64_t n, cudaStream_t s);
+template <typename T> cudaError_t plan_unpermute(const T* staged, const uint32_t* inv, T* out, int64_t n, int ct, cudaStream_t s);
+
 // Specialised kernels.  Return true when they handled the evaluation (err holds the launch
 // status), false when the configuration is outside their envelope.
 template <typename T> bool try_eval_fast_unstructured(const EvalParams<T>& P, cudaStream_t s, const char** name,

@@ -44,7 +44,36 @@ __global__ void __launch_bounds__(BLOCK) plan_gather_kernel(const T* __restrict_
     if (k < n) dst[k] = src[perm[k]];
 }
 
+__global__ void __launch_bounds__(BLOCK) plan_inverse_kernel(const uint32_t* __restrict__ perm, uint32_t* __restrict__ inv, int64_t n) {
+    const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (k < n) inv[perm[k]] = (uint32_t)k;
+}
+
+// out[i + cc * n] = staged[inv[i] * ct + cc]: one random (ct * sizeof(T))-byte read per point, coalesced
+// writes — instead of ct random read-modify-write sector accesses per point for a direct scatter.
+template <typename T>
+__global__ void __launch_bounds__(BLOCK) plan_unpermute_kernel(const T* __restrict__ staged, const uint32_t* __restrict__ inv,
+                                                               T* __restrict__ out, int64_t n, int ct) {
+    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= n) return;
+    const T* src = staged + (int64_t)__ldcs(inv + i) * ct;
+    for (int cc = 0; cc < ct; ++cc) __stcs(out + i + (int64_t)cc * n, __ldcs(src + cc));
+}
+
 }  // namespace
+
+cudaError_t plan_inverse(const uint32_t* perm, uint32_t* inv, int64_t n, cudaStream_t s) {
+    plan_inverse_kernel<<<(unsigned)((n + BLOCK - 1) / BLOCK), BLOCK, 0, s>>>(perm, inv, n);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t plan_unpermute(const T* staged, const uint32_t* inv, T* out, int64_t n, int ct, cudaStream_t s) {
+    plan_unpermute_kernel<T><<<(unsigned)((n + BLOCK - 1) / BLOCK), BLOCK, 0, s>>>(staged, inv, out, n, ct);
+    return cudaGetLastError();
+}
+template cudaError_t plan_unpermute<float>(const float*, const uint32_t*, float*, int64_t, int, cudaStream_t);
+template cudaError_t plan_unpermute<double>(const double*, const uint32_t*, double*, int64_t, int, cudaStream_t);
 
 template <typename T>
 cudaError_t plan_sort_points(const EvalParams<T>& P, uint32_t* perm, T* const* t_sorted, void* scratch,

@@ -70,6 +70,10 @@ extern "C" {
                                     * and cached until t_eval, the knots or size(u) change — the analogue of the
                                     * reference's idx_eval / basis_function_eval caches.  Results are written to
                                     * their original positions: `out` is identical to the unsorted evaluation. */
+#define DIND_FLAG_PLAN_ORDER 32u  /* with DIND_FLAG_CELL_SORTED: leave `out` in plan order (row k of out belongs to
+                                    * original point perm[k], see dind_get_plan_permutation) instead of scattering
+                                    * every result to its original position — the 4/8-byte scatter is what bounds
+                                    * the sorted path (random read-modify-write of 32-byte sectors). */
 
 #define DIND_MAX_DIMS 8   /* N_in <= 8 */
 #define DIND_MAX_DEGREE 7 /* B-spline degree <= 7 */
@@ -152,6 +156,9 @@ int dind_get_knots_all(dind_handle_t handle, int dim, void* knots_out /* host */
 /* basis_function_eval[n_eval, degree+1, max_derivative_order_eval+1] (column-major), computed
  * on the device on demand (src/spline_utils.jl:174-191). */
 int dind_get_basis_function_eval(dind_handle_t handle, int dim, void* basis_out /* host */);
+/* The cell-sorted plan's permutation (n_points entries, host or device pointer): plan position k
+ * holds original point perm[k].  Valid after an evaluation with DIND_FLAG_CELL_SORTED. */
+int dind_get_plan_permutation(dind_handle_t handle, uint32_t* perm_out);
 /* Name of the kernel family the last evaluation on this handle dispatched to. */
 const char* dind_last_kernel(dind_handle_t handle);
 /* Number of kernel launches issued by this handle so far. */

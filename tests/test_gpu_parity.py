@@ -468,3 +468,17 @@ def test_fused_gradient_rejects_constant_and_nurbs(D):
     with pytest.raises(AssertionError):
         D.eval_unstructured_gradient(itp)
     itp.close()
+
+
+def test_plan_order_output_and_permutation(D):
+    rng = np.random.default_rng(9)
+    kinds, degrees = ("bspline",) * 2, (3, 2)
+    ts, u, _ = _case(rng, kinds, degrees, (9, 8), (2,), np.float64)
+    xs = H.zipped_queries(rng, ts, 5000, np.float64)
+    itp = D.NDInterpolation(u, H.make_dims(D, kinds, ts, xs, degrees, None, max_deriv=[0, 0]))
+    ref = D.eval_unstructured(itp)
+    got = D.eval_unstructured(itp, flags=CELL_SORTED | 32)      # DIND_FLAG_PLAN_ORDER
+    perm = itp.plan_permutation()
+    assert sorted(perm.tolist()) == list(range(xs[0].size))
+    assert np.array_equal(got, ref[perm])
+    itp.close()
