@@ -297,6 +297,18 @@ def run_gpu(args, wl, rank, world, local_rank):
             else:
                 D.eval_unstructured_(out, itp, flags=uflags)
 
+    if args.gather and world > 1:
+        # optional NCCL all-gather of the outputs after the kernel (north_star (5)): never inside the kernel loop
+        inner_step = step
+        n_total = (wl.n_grid[-1] if wl.grid else out.shape[0]) * world
+
+        def step(i):
+            inner_step(i)
+            if wl.grid:
+                D.gather_grid(out, len(wl.n_grid), n_total)
+            else:
+                D.gather_unstructured(out, n_total)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -377,7 +389,7 @@ def run_gpu(args, wl, rank, world, local_rank):
         "config": {"workload": wl.name, "points_per_step_per_gpu": wl.points_per_step(),
                    "sharding": ("slab along the last grid axis" if wl.grid else "contiguous index range") + ", u/knots replicated, no collective",
                    "l2": f"working set exceeds L2 (126 MB): output streamed, u rotates over {wl.n_u_buffers} buffers" if wl.grid else "t_eval + out exceed L2",
-                   "kernel": kernel, "gradient": args.gradient, "point_order": ("iid random, evaluated through the cell-sorted plan" + (", output left in plan order" if args.plan_order else "") if args.sorted else "iid random") if not wl.grid else "grid"},
+                   "kernel": kernel, "gradient": args.gradient, "all_gather_outputs": bool(args.gather and world > 1), "point_order": ("iid random, evaluated through the cell-sorted plan" + (", output left in plan order" if args.plan_order else "") if args.sorted else "iid random") if not wl.grid else "grid"},
         "e2e": {"value": round(pts_step_all / (e2e_ms * 1e-3) / 1e9, 4), "unit": "Gpoints/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "host (pinned) buffers through the public API; synchronous call incl. H2D + kernel + D2H"},
@@ -484,6 +496,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gradient", choices=["fused", "separate"], default=None,
                     help="unstructured workloads: a step evaluates value + all first partials (one fused pass, or N_in+1 calls)")
+    ap.add_argument("--gather", action="store_true", help="N > 1: all-gather the outputs (NCCL) inside the timed step")
     ap.add_argument("--plan-order", action="store_true", help="with --sorted: leave the output in plan order (no scatter)")
     ap.add_argument("--sorted", action="store_true", help="unstructured workloads: evaluate through the cell-sorted plan")
     args = ap.parse_args()
