@@ -23,6 +23,20 @@ __global__ void fill_pencil(float* out, int RV, long R, int chunk) {
         if (CS) __stcs((float4*)op, v); else *(float4*)op = v;
     }
 }
+// pencil-pattern stores + L2-resident reads of a 67 MB array (about the read volume of the real kernel)
+__global__ void fill_pencil_reads(float* out, const float* __restrict__ u, int RV, long R, int chunk) {
+    int rv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rv >= RV) return;
+    float* op = out + (long)rv * 4 + (long)blockIdx.y * chunk * R;
+    // u index: row of 256 floats per (j, k) pair, like a 2x-upsampled trilinear read
+    const int i = (rv % 128) * 2, j = (rv / 128) / 2;
+    for (int g = 0; g < chunk; ++g, op += R) {
+        const int k = (blockIdx.y * chunk + g) / 2;
+        const float* p = u + ((long)k * 256 + j) * 256 + i;
+        float a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        __stcs((float4*)op, make_float4(a, a + b, b, b + c));
+    }
+}
 // persistent grid-stride copy for reference
 __global__ void copy_k(const float4* __restrict__ in, float4* __restrict__ out, size_t n4) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i];
@@ -54,6 +68,13 @@ int main() {
         time(nm, [&] { fill_pencil<true><<<g, 128>>>(b, RV, R, chunk); }, n * 4.0);
         snprintf(nm, 64, "fill pencil plain chunk=%d", chunk);
         time(nm, [&] { fill_pencil<false><<<g, 128>>>(b, RV, R, chunk); }, n * 4.0);
+    }
+    for (int chunk : {32, 64}) {
+        int RV = 512 * 512 / 4; long R = 512 * 512;
+        dim3 g((RV + 127) / 128, 512 / chunk);
+        char nm[64];
+        snprintf(nm, 64, "pencil stores + reads chunk=%d", chunk);
+        time(nm, [&] { fill_pencil_reads<<<g, 128>>>(b, a, RV, R, chunk); }, n * 4.0 + 67108864.0);
     }
     time("copy grid-stride (r+w)", [&] { copy_k<<<148 * 8, 256>>>((const float4*)a, (float4*)b, n4); }, n * 8.0);
     time("cudaMemcpy D2D (r+w)", [&] { cudaMemcpyAsync(b, a, n * 4, cudaMemcpyDeviceToDevice); }, n * 8.0);
