@@ -239,7 +239,7 @@ __device__ __forceinline__ void walk_pencil(const EvalParams<T>& P, const Pencil
 // One warp = one work item: 32*VX consecutive g_1 x J consecutive g_2 at fixed middle axes,
 // over `chunk` coordinates of the last axis.
 template <typename T, int N, int W, int VX, int J, bool NURBS, bool FULL, bool PF>
-__global__ void __launch_bounds__(PBLOCK, PF ? 5 : 8) grid_pencil_kernel(const __grid_constant__ EvalParams<T> P, int n_items, int nseg,
+__global__ void __launch_bounds__(PBLOCK, PF ? 5 : ((sizeof(T) == 8 || W >= 3 || N >= 4) ? 4 : 8)) grid_pencil_kernel(const __grid_constant__ EvalParams<T> P, int n_items, int nseg,
                                                              int n2g, int chunk, int l2_warm) {
     using Ctx = PencilCtx<T, N, W, VX, J>;
     __shared__ int s_i0[MAXCHUNK];
