@@ -31,6 +31,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "Gpoints/s"
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+# `ncu --set full` captures (profiles/r1_<workload>.md); None where no capture exists.
+NCU_TRAFFIC = {"c2": 561_484_544, "c4": 2_575_898_664, "c1": 16_083_456, "c3": 1_015_403_008, "c5": 184_760_204_000}
+
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -50,9 +54,6 @@ class Workload:
     dtype = np.float32
     kinds = ()
     degrees = None
-
-    def host_inputs(self, rank, world):
-        raise NotImplementedError
 
 
 class Grid(Workload):
@@ -395,7 +396,7 @@ def run_gpu(args, wl, rank, world, local_rank):
                 "note": "host (pinned) buffers through the public API; synchronous call incl. H2D + kernel + D2H"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None, "peak_source": peak_src,
+                     "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": NCU_TRAFFIC.get(wl.key), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": wl.alg_bytes()},
         "clocks": clocks.summary(),
     }

@@ -75,6 +75,13 @@ int main() {
         char nm[64];
         snprintf(nm, 64, "pencil stores + reads chunk=%d", chunk);
         time(nm, [&] { fill_pencil_reads<<<g, 128>>>(b, a, RV, R, chunk); }, n * 4.0 + 67108864.0);
+        // same with residency limited by dynamic shared memory (like the real kernel's 5 CTAs = 20 warps / SM)
+        for (int ctas : {12, 8, 5, 3}) {
+            int smem = (227 * 1024) / ctas - 1024;
+            cudaFuncSetAttribute(fill_pencil_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            snprintf(nm, 64, "  ... %d CTAs/SM chunk=%d", ctas, chunk);
+            time(nm, [&] { fill_pencil_reads<<<g, 128, smem>>>(b, a, RV, R, chunk); }, n * 4.0 + 67108864.0);
+        }
     }
     time("copy grid-stride (r+w)", [&] { copy_k<<<148 * 8, 256>>>((const float4*)a, (float4*)b, n4); }, n * 8.0);
     time("cudaMemcpy D2D (r+w)", [&] { cudaMemcpyAsync(b, a, n * 4, cudaMemcpyDeviceToDevice); }, n * 8.0);
