@@ -447,7 +447,7 @@ bool try_grid_range(const EvalParams<T>& P0, cudaStream_t s, const char** name, 
     // between axis 2 and the last axis become "point" axes behind them.
     int W = 1;
     for (int d = 0; d < NT; ++d) W = max(W, P0.dim[d].width);
-    if (W < 2 || W > 4) return false;
+    if (W < 1 || W > 4) return false;   // W = 1: all-Constant dimensions (nearest-node lookup)
     EvalParams<T> P = P0;
     int ns = 0, np = 0;
     int point[MAXN];
@@ -474,6 +474,7 @@ bool try_grid_range(const EvalParams<T>& P0, cudaStream_t s, const char** name, 
         *name = np ? "grid_pencil<N=" #NN "+point axes,W=" #WW ">" : "grid_pencil<N=" #NN ",W=" #WW ">"; \
         return true;                                                  \
     }
+    DIND_PENCIL(2, 1) DIND_PENCIL(3, 1) DIND_PENCIL(4, 1) DIND_PENCIL(5, 1)
     DIND_PENCIL(2, 2) DIND_PENCIL(2, 3) DIND_PENCIL(2, 4)
     DIND_PENCIL(3, 2) DIND_PENCIL(3, 3) DIND_PENCIL(3, 4)
     DIND_PENCIL(4, 2) DIND_PENCIL(4, 3) DIND_PENCIL(4, 4)

@@ -64,3 +64,4 @@ if __name__ == "__main__":
     run("3-D trilinear F32 256^3 -> 500x333x250 (odd)", ["linear"] * 3, [0] * 3, (256,) * 3, (500, 333, 250), f32)
     run("4-D linear F32 64^4 -> 128^4", ["linear"] * 4, [0] * 4, (64,) * 4, (128,) * 4, f32)
     run("3-D const x lin x lin F32 (generic path)", ["constant", "linear", "linear"], [0] * 3, (128,) * 3, (256,) * 3, f32)
+    run("3-D all-Constant F32 256^3 -> 512^3", ["constant"] * 3, [0] * 3, (256,) * 3, (512,) * 3, f32)
