@@ -290,13 +290,15 @@ class NDInterpolation:
         self.set_u(u)
 
     # -- data ------------------------------------------------------------------------------
-    def set_u(self, u):
-        """Swap in a new `u` of the same shape (re-evaluation with the t_eval caches kept)."""
+    def set_u(self, u, flags=0):
+        """Swap in a new `u` of the same shape (re-evaluation with the t_eval caches kept).
+        flags=1 (DIND_FLAG_ASYNC) with a pinned host array: the upload is only queued — keep `u`
+        unchanged until `synchronize()`."""
         a = _Arr(u, self.dtype)
         if len(a.shape) - self.N_in != self.N_out:
             raise DindError(_lib.ERR_SIZE_MISMATCH, "u changed its number of dimensions")
         dims = (C.c_int64 * len(a.shape))(*a.shape)
-        _lib.check(self._h.lib.dind_set_u(self._h.h, C.c_void_p(a.ptr), dims, len(a.shape), 0))
+        _lib.check(self._h.lib.dind_set_u(self._h.h, C.c_void_p(a.ptr), dims, len(a.shape), int(flags)))
         self._h.keep["u"] = a
         self.u = u
         self._u_on_device = a.device
@@ -310,6 +312,10 @@ class NDInterpolation:
 
     def set_stream(self, stream_ptr):
         self._h.set_stream(stream_ptr)
+
+    def synchronize(self):
+        """Wait for everything queued with DIND_FLAG_ASYNC (kernels and host copies)."""
+        _lib.check(self._h.lib.dind_synchronize(self._h.h))
 
     @property
     def output_size(self):   # get_output_size (interpolation_utils.jl:77-79)

@@ -122,7 +122,10 @@ struct dind_interp_s {
     DevBuf plan_perm, plan_inv, plan_stage;
     DevBuf plan_t[MAXN];
     // staging
-    DevBuf out_stage;
+    DevBuf out_stage[2];            // host `out`: device staging, double buffered for the pipelined (ASYNC) path
+    int out_toggle = 0;
+    cudaStream_t copy_stream = nullptr;   // D2H of results, so that it overlaps the next step's H2D + kernel
+    cudaEvent_t ev_kernel = nullptr, ev_d2h[2] = {nullptr, nullptr};
     DevBuf pts_stage[MAXN];
     std::string last_kernel = "none";
     int64_t launches = 0;
@@ -343,14 +346,24 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         if (D.kind == LINEAR && orders[d] > 1) zero_result = true;
     }
     const bool out_on_device = is_device_ptr(out);
-    if ((flags & DIND_FLAG_ASYNC) && !out_on_device)
-        return fail(DIND_ERR_INVALID_ARGUMENT, "DIND_FLAG_ASYNC needs a device `out` pointer");
+    // DIND_FLAG_ASYNC with a HOST `out` (pinned memory): the D2H copy is queued on the handle's copy
+    // stream and the call returns; the caller reads `out` after dind_synchronize.  Two staging buffers
+    // let the copy of step i overlap the H2D + kernel of step i + 1.
+    const bool pipelined = (flags & DIND_FLAG_ASYNC) && !out_on_device;
+    if (pipelined && !h->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_kernel, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
+    }
+    const int sb = pipelined ? (h->out_toggle ^= 1) : 0;
     const size_t out_bytes = (size_t)n_points * h->n_comp * sizeof(T) * (gradient ? N + 1 : 1);
     T* d_out = (T*)out;
     const bool untouched_semantics = const_deriv && h->u_dims.size() > (size_t)N;
     if (!out_on_device) {
-        CUDA_TRY(h->out_stage.ensure(out_bytes));
-        d_out = (T*)h->out_stage.p;
+        if (pipelined) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_d2h[sb], 0));   // this buffer's previous D2H is done
+        else if (h->copy_stream) CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+        CUDA_TRY(h->out_stage[sb].ensure(out_bytes));
+        d_out = (T*)h->out_stage[sb].p;
         // Constant-with-derivative leaves vector outputs untouched off the knots
         // (src/interpolation_methods.jl:49-55): keep the caller's values.
         if (untouched_semantics) CUDA_TRY(cudaMemcpyAsync(d_out, out, out_bytes, cudaMemcpyHostToDevice, h->stream));
@@ -473,7 +486,12 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         CUDA_TRY(plan_unpermute<T>((const T*)h->plan_stage.p, (const uint32_t*)h->plan_inv.p, d_out, n_points, unperm_ct, h->stream));
         h->launches += 1;
     }
-    if (!out_on_device) {
+    if (pipelined) {
+        CUDA_TRY(cudaEventRecord(h->ev_kernel, h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_kernel, 0));
+        CUDA_TRY(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+        CUDA_TRY(cudaEventRecord(h->ev_d2h[sb], h->copy_stream));
+    } else if (!out_on_device) {
         CUDA_TRY(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
     } else if (!(flags & DIND_FLAG_ASYNC)) {
@@ -577,7 +595,10 @@ int dind_destroy(dind_handle_t h) {
         h->dims[d].release();
         h->pts_stage[d].release();
     }
-    h->u_owned.release(); h->w_owned.release(); h->uw.release(); h->u_aos.release(); h->out_stage.release();
+    h->u_owned.release(); h->w_owned.release(); h->uw.release(); h->u_aos.release(); h->out_stage[0].release(); h->out_stage[1].release();
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->ev_kernel) cudaEventDestroy(h->ev_kernel);
+    for (int i = 0; i < 2; ++i) if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
     h->plan_perm.release(); h->plan_inv.release(); h->plan_stage.release();
     for (int d = 0; d < MAXN; ++d) h->plan_t[d].release();
     delete h;
@@ -595,6 +616,7 @@ int dind_synchronize(dind_handle_t h) {
     int rc = check_handle(h);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->copy_stream) CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
     return DIND_OK;
 }
 
@@ -721,7 +743,9 @@ int dind_set_u(dind_handle_t h, const void* u, const int64_t* dims, int ndims, u
     } else {
         CUDA_TRY(h->u_owned.ensure(bytes));
         CUDA_TRY(cudaMemcpyAsync(h->u_owned.p, u, bytes, is_device_ptr(u) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
-        if (!is_device_ptr(u)) CUDA_TRY(cudaStreamSynchronize(h->stream));   // pageable source may be reused by the caller
+        // host source: wait unless the caller promises (DIND_FLAG_ASYNC) to keep the — pinned — buffer unchanged
+        // until the next dind_synchronize
+        if (!is_device_ptr(u) && !(flags & DIND_FLAG_ASYNC)) CUDA_TRY(cudaStreamSynchronize(h->stream));
         h->d_u = h->u_owned.p;
     }
     if (!h->u_set || h->u_dims.size() != (size_t)ndims || !std::equal(dims, dims + ndims, h->u_dims.begin())) h->plan_valid = false;

@@ -60,7 +60,10 @@ extern "C" {
 #define DIND_BSPLINE 2
 
 /* flags */
-#define DIND_FLAG_ASYNC 1u       /* do not wait for the stream before returning (device `out` only) */
+#define DIND_FLAG_ASYNC 1u       /* do not wait before returning.  Device `out`: the kernel is queued on the stream.
+                                   * Host `out` / host `u` (PINNED memory): the copies are queued too — D2H on the
+                                   * handle's copy stream, overlapping the next step's H2D + kernel — and the
+                                   * buffers belong to the library until dind_synchronize returns. */
 #define DIND_FLAG_COPY 2u        /* copy device data instead of borrowing it                           */
 #define DIND_FLAG_CACHED_IDX 4u  /* eval_unstructured: read the idx_eval cache instead of searching   */
 #define DIND_FLAG_GENERIC 8u     /* force the generic (any-N, any-degree) kernels; testing/reference  */

@@ -482,3 +482,31 @@ def test_plan_order_output_and_permutation(D):
     assert sorted(perm.tolist()) == list(range(xs[0].size))
     assert np.array_equal(got, ref[perm])
     itp.close()
+
+
+def test_pipelined_async_host_buffers(D):
+    """DIND_FLAG_ASYNC with pinned host u / out: copies are queued (D2H on the copy stream), results are
+    valid after synchronize() and equal the synchronous calls."""
+    import torch
+    rng = np.random.default_rng(12)
+    ts = [H.knots(rng, 20, np.float32) for _ in range(3)]
+    xs = [np.linspace(t[0], t[-1], 48).astype(np.float32) for t in ts]
+    us = [torch.rand((20, 20, 20)).pin_memory() for _ in range(4)]
+    u_np = [u.numpy().transpose(2, 1, 0) for u in us]
+    outs = [torch.empty((48, 48, 48)).pin_memory() for _ in range(2)]
+    out_np = [o.numpy().transpose(2, 1, 0) for o in outs]
+    itp = D.NDInterpolation(u_np[0], tuple(D.LinearInterpolationDimension(t, t_eval=x) for t, x in zip(ts, xs)))
+    ref = []
+    for k in range(4):
+        itp.set_u(u_np[k])
+        ref.append(np.array(D.eval_grid(itp)))
+    got = []
+    for k in range(4):
+        itp.set_u(u_np[k], flags=1)
+        D.eval_grid_(out_np[k % 2], itp, flags=1)
+        if k % 2 == 1:          # both buffers in flight: drain and check
+            itp.synchronize()
+            got += [np.array(out_np[0]), np.array(out_np[1])]
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+    itp.close()
