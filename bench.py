@@ -407,7 +407,10 @@ def run_gpu(args, wl, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": wl.dtype_name, "data": "synthetic",
         "config": {"workload": wl.name, "points_per_step_per_gpu": wl.points_per_step(),
-                   "sharding": ("slab along the last grid axis" if wl.grid else "contiguous index range") + ", u/knots replicated, no collective",
+                   "sharding": (("slab along the last grid axis" if wl.grid else "contiguous index range") + ", u/knots replicated, no collective"
+                                + (f"; weak scaling: u fixed, the global grid's last axis has {world}x the points, so every rank writes the same number of "
+                                   f"outputs but samples its part of the last axis {world}x more densely (fewer window updates per output: per-GPU "
+                                   f"throughput rises slightly with N)" if wl.grid and world > 1 else "")),
                    "l2": f"working set exceeds L2 (126 MB): output streamed, u rotates over {wl.n_u_buffers} buffers" if wl.grid else "t_eval + out exceed L2",
                    "kernel": kernel, "first_call_ms_incl_cache_build": round(first_call_ms, 3), "gradient": args.gradient, "all_gather_outputs": bool(args.gather and world > 1), "point_order": ("iid random, evaluated through the cell-sorted plan" + (", output left in plan order" if args.plan_order else "") if args.sorted else "iid random") if not wl.grid else "grid"},
         "e2e": {"value": round(pts_step_all / (e2e_ms * 1e-3) / 1e9, 4), "unit": "Gpoints/s",
