@@ -18,7 +18,8 @@ export NDInterpolation, LinearInterpolationDimension, ConstantInterpolationDimen
     BSplineInterpolationDimension, NURBSWeights, EmptyCache,
     eval_unstructured, eval_unstructured!, eval_grid, eval_grid!, eval_unstructured_gradient!
 
-const libdind = Ref{String}(get(ENV, "LIBDIND", joinpath(@__DIR__, "..", "..", "..", "libdind.so")))
+# a const String: `ccall((:sym, libdind), ...)` needs a constant library expression
+const libdind = get(ENV, "LIBDIND", joinpath(@__DIR__, "..", "..", "..", "libdind.so"))
 
 const DIND_F32, DIND_F64 = Cint(0), Cint(1)
 const DIND_LINEAR, DIND_CONSTANT, DIND_BSPLINE = Cint(0), Cint(1), Cint(2)
@@ -30,7 +31,7 @@ dind_dtype(T) = throw(ArgumentError("libdind supports Float32 and Float64, got $
 # Every validation failure of the reference is an `@assert`; a negative status maps to the same.
 function check(rc::Cint)
     rc == 0 && return nothing
-    msg = unsafe_string(ccall((:dind_last_error, libdind[]), Cstring, ()))
+    msg = unsafe_string(ccall((:dind_last_error, libdind), Cstring, ()))
     throw(AssertionError("[dind $rc] $msg"))
 end
 
@@ -105,31 +106,31 @@ mutable struct NDInterpolation{N_in, N_out, T, ID <: AbstractInterpolationDimens
     handle::Ptr{Cvoid}
 end
 
-function NDInterpolation(u::AbstractArray{T}, interp_dims, cache = EmptyCache(); device::Integer = 0) where {T}
+function NDInterpolation(u::AbstractArray{T}, interp_dims, cache::AbstractInterpolationCache; device::Integer = 0) where {T}
     interp_dims isa AbstractInterpolationDimension && (interp_dims = (interp_dims,))
     N_in = length(interp_dims)
     N_out = ndims(u) - N_in
     @assert N_out ≥ 0 "The number of dimensions of u must be at least the number of interpolation dimensions."
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:dind_create, libdind[]), Cint, (Ptr{Ptr{Cvoid}}, Cint, Cint, Cint), h, N_in, dind_dtype(T), device))
+    check(ccall((:dind_create, libdind), Cint, (Ptr{Ptr{Cvoid}}, Cint, Cint, Cint), h, N_in, dind_dtype(T), device))
     itp = NDInterpolation{N_in, N_out, T, eltype(interp_dims), typeof(cache), typeof(u)}(u, Tuple(interp_dims), cache, h[])
-    finalizer(x -> ccall((:dind_destroy, libdind[]), Cint, (Ptr{Cvoid},), x.handle), itp)
+    finalizer(x -> ccall((:dind_destroy, libdind), Cint, (Ptr{Cvoid},), x.handle), itp)
     for (d, dim) in enumerate(interp_dims)
         t = convert(Vector{T}, dim.t)
         mult = dim isa BSplineInterpolationDimension ? convert(Vector{Int64}, dim.multiplicities) : Int64[]
-        GC.@preserve t mult check(ccall((:dind_set_dim, libdind[]), Cint,
+        GC.@preserve t mult check(ccall((:dind_set_dim, libdind), Cint,
             (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Int64, Cint, Ptr{Int64}, Cint),
             itp.handle, d - 1, kind(dim), t, length(t), degree(dim),
             isempty(mult) ? C_NULL : pointer(mult), dim isa ConstantInterpolationDimension ? dim.left : true))
         te = convert(Vector{T}, dim.t_eval)      # a CuArray would be passed as a device pointer instead (zero-copy)
-        GC.@preserve te check(ccall((:dind_set_t_eval, libdind[]), Cint,
+        GC.@preserve te check(ccall((:dind_set_t_eval, libdind), Cint,
             (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64, Cint, Cuint),
             itp.handle, d - 1, isempty(te) ? C_NULL : pointer(te), length(te), max_deriv(dim), 0))
     end
     if cache isa NURBSWeights
         w = convert(Array{T}, cache.weights)
         dims = collect(Int64, size(w))
-        GC.@preserve w dims check(ccall((:dind_set_weights, libdind[]), Cint,
+        GC.@preserve w dims check(ccall((:dind_set_weights, libdind), Cint,
             (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Cint, Cuint), itp.handle, w, dims, length(dims), 0))
     end
     set_u!(itp, u)
@@ -140,7 +141,7 @@ NDInterpolation(u, interp_dims; cache = EmptyCache(), kwargs...) = NDInterpolati
 "Swap in a new `u` (re-evaluation with the cached t_eval indices/weights kept)."
 function set_u!(itp::NDInterpolation{N_in, N_out, T}, u::AbstractArray{T}) where {N_in, N_out, T}
     dims = collect(Int64, size(u))
-    GC.@preserve u dims check(ccall((:dind_set_u, libdind[]), Cint,
+    GC.@preserve u dims check(ccall((:dind_set_u, libdind), Cint,
         (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Cint, Cuint), itp.handle, u, dims, length(dims), 0))
     itp.u = u
     return itp
@@ -151,13 +152,13 @@ get_output_size(itp::NDInterpolation{N_in}) where {N_in} = size(itp.u)[(N_in + 1
 # idx_eval / basis_function_eval are computed on the device on demand (fields of the reference structs)
 function idx_eval(itp::NDInterpolation, d::Integer)
     out = Vector{Int64}(undef, length(itp.interp_dims[d].t_eval))
-    check(ccall((:dind_get_idx_eval, libdind[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}), itp.handle, d - 1, out))
+    check(ccall((:dind_get_idx_eval, libdind), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}), itp.handle, d - 1, out))
     return out
 end
 function basis_function_eval(itp::NDInterpolation{N_in, N_out, T}, d::Integer) where {N_in, N_out, T}
     dim = itp.interp_dims[d]
     out = Array{T, 3}(undef, length(dim.t_eval), dim.degree + 1, dim.max_derivative_order_eval + 1)
-    check(ccall((:dind_get_basis_function_eval, libdind[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), itp.handle, d - 1, out))
+    check(ccall((:dind_get_basis_function_eval, libdind), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), itp.handle, d - 1, out))
     return out
 end
 
@@ -169,7 +170,7 @@ function eval_unstructured!(out::AbstractArray{T}, itp::NDInterpolation{N_in, N_
     @assert size(out, 1) == length(first(itp.interp_dims).t_eval) "The t_eval of all interpolation dimensions must have the same length as the first dimension of out."
     @assert size(out)[2:end] == get_output_size(itp) "The size of the last N_out dimensions of out must be the same as the output size of the interpolation."
     o = orders_arg(derivative_orders)
-    GC.@preserve out o check(ccall((:dind_eval_unstructured, libdind[]), Cint,
+    GC.@preserve out o check(ccall((:dind_eval_unstructured, libdind), Cint,
         (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cint}, Cuint), itp.handle, out, o, 0))
     return out
 end
@@ -183,7 +184,7 @@ function eval_grid!(out::AbstractArray{T}, itp::NDInterpolation{N_in, N_out, T};
     @assert all(i -> size(out, i) == length(itp.interp_dims[i].t_eval), 1:N_in) "For the first N_in dimensions of out the length must match the t_eval of the corresponding interpolation dimension."
     @assert size(out)[(N_in + 1):end] == get_output_size(itp) "The size of the last N_out dimensions of out must be the same as the output size of the interpolation."
     o = orders_arg(derivative_orders)
-    GC.@preserve out o check(ccall((:dind_eval_grid, libdind[]), Cint,
+    GC.@preserve out o check(ccall((:dind_eval_grid, libdind), Cint,
         (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cint}, Cuint), itp.handle, out, o, 0))
     return out
 end
@@ -201,7 +202,7 @@ end
 """
 function eval_unstructured_gradient!(out::AbstractArray{T}, itp::NDInterpolation{N_in, N_out, T}) where {N_in, N_out, T}
     @assert size(out) == (length(first(itp.interp_dims).t_eval), get_output_size(itp)..., N_in + 1)
-    GC.@preserve out check(ccall((:dind_eval_unstructured_gradient, libdind[]), Cint,
+    GC.@preserve out check(ccall((:dind_eval_unstructured_gradient, libdind), Cint,
         (Ptr{Cvoid}, Ptr{Cvoid}, Cuint), itp.handle, out, 0))
     return out
 end
@@ -213,7 +214,7 @@ function (itp::NDInterpolation{N_in, N_out, T})(out::AbstractArray{T}, t::Tuple{
     pts = [T[ti] for ti in t]
     ptrs = Ptr{Cvoid}[pointer(p) for p in pts]
     o = orders_arg(derivative_orders)
-    GC.@preserve out pts ptrs o check(ccall((:dind_eval_points, libdind[]), Cint,
+    GC.@preserve out pts ptrs o check(ccall((:dind_eval_points, libdind), Cint,
         (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Int64, Ptr{Cint}, Cuint), itp.handle, out, ptrs, 1, o, 0))
     return out
 end
