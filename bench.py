@@ -333,8 +333,32 @@ def run_gpu(args, wl, rank, world, local_rank):
         ev1.record(stream)
         barrier()
     ms_total = ev0.elapsed_time(ev1)
+    ms_per_step_rank = ms_total / args.steps
     launches = itp.launch_count - l0
     kernel = itp.last_kernel
+
+    # ---- cache construction as its own timed path: new t_eval (borrowed device pointers) ->
+    # everything the evaluation needs that depends on t_eval.  Grids: the per-axis tables; unstructured: the
+    # cell-sorted plan (key kernel + radix sort + sorted copies of t_eval + inverse permutation).
+    cache_build = None
+    if world == 1 and not args.no_cache_build:
+        t_cur = [d.t_eval for d in itp.interp_dims]
+        cb_flags = 1 | (0 if wl.grid else 16)
+        # timed on the host clock around a device synchronisation: cache construction includes host-side work
+        # (scratch allocation for the radix sort) that a stream event would not see
+        reps, cb_times = 5, []
+        for r in range(reps + 1):
+            torch.cuda.synchronize()
+            _t0 = time.perf_counter()
+            itp.set_t_eval(t_cur)
+            itp.build_caches(grid=wl.grid, flags=cb_flags)
+            torch.cuda.synchronize()
+            cb_times.append((time.perf_counter() - _t0) * 1e3)
+        cb_ms = float(np.median(cb_times[1:]))
+        n_cb = sum(int(t.shape[0]) for t in t_cur) if wl.grid else int(t_cur[0].shape[0])
+        cache_build = {"ms": round(cb_ms, 4), "what": "per-axis index/weight tables" if wl.grid else "cell-sorted plan (keys, radix sort, sorted t_eval copies, inverse permutation)",
+                       "entries": n_cb, "Gentries_per_s": round(n_cb / (cb_ms * 1e-3) / 1e9, 4),
+                       "evaluations_to_amortise": round(cb_ms / ms_per_step_rank, 2) if not wl.grid else None}
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
     e2e_ms, h2d, d2h = None, 0, 0
@@ -412,7 +436,7 @@ def run_gpu(args, wl, rank, world, local_rank):
                                    f"outputs but samples its part of the last axis {world}x more densely (fewer window updates per output: per-GPU "
                                    f"throughput rises slightly with N)" if wl.grid and world > 1 else "")),
                    "l2": f"working set exceeds L2 (126 MB): output streamed, u rotates over {wl.n_u_buffers} buffers" if wl.grid else "t_eval + out exceed L2",
-                   "kernel": kernel, "first_call_ms_incl_cache_build": round(first_call_ms, 3), "gradient": args.gradient, "all_gather_outputs": bool(args.gather and world > 1), "point_order": ("iid random, evaluated through the cell-sorted plan" + (", output left in plan order" if args.plan_order else "") if args.sorted else "iid random") if not wl.grid else "grid"},
+                   "kernel": kernel, "first_call_ms_incl_cache_build": round(first_call_ms, 3), "cache_build": cache_build, "gradient": args.gradient, "all_gather_outputs": bool(args.gather and world > 1), "point_order": ("iid random, evaluated through the cell-sorted plan" + (", output left in plan order" if args.plan_order else "") if args.sorted else "iid random") if not wl.grid else "grid"},
         "e2e": {"value": round(pts_step_all / (e2e_ms * 1e-3) / 1e9, 4), "unit": "Gpoints/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "host (pinned) buffers through the public API, H2D + kernel + D2H every step; grid workloads queue the steps (DIND_FLAG_ASYNC) so D2H(i) overlaps H2D(i+1)",
@@ -518,6 +542,7 @@ def main():
     ap.add_argument("--full", action="store_true", help="full-size point counts for c3 / c5")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink c2 (debugging only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cache-build", action="store_true", help="skip the separate timing of cache construction")
     ap.add_argument("--gradient", choices=["fused", "separate"], default=None,
                     help="unstructured workloads: a step evaluates value + all first partials (one fused pass, or N_in+1 calls)")
     ap.add_argument("--gather", action="store_true", help="N > 1: all-gather the outputs (NCCL) inside the timed step")

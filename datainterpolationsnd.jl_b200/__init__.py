@@ -106,6 +106,9 @@ class AbstractInterpolationDimension:
             self.t = self.t.astype(np.float64)
         if self.t.size > 1 and not np.all(np.diff(self.t) > 0):   # validate_t (interpolation_utils.jl:34-37)
             raise DindError(_lib.ERR_INVALID_ARGUMENT, "The elements of t must be sorted and unique.")
+        self.set_t_eval(t_eval)
+
+    def set_t_eval(self, t_eval):
         if t_eval is None:
             t_eval = np.empty(0, dtype=self.t.dtype)   # similar(t, 0)
         elif not _is_torch(t_eval):
@@ -290,6 +293,18 @@ class NDInterpolation:
         self.set_u(u)
 
     # -- data ------------------------------------------------------------------------------
+    def set_t_eval(self, t_evals):
+        """Swap in new evaluation points for every dimension (the reference rebuilds the dimension
+        structs for that: `t_eval` is a constructor keyword).  All caches that depend on t_eval are
+        dropped and rebuilt lazily, or explicitly by `build_caches`."""
+        t_evals = tuple(t_evals)
+        if len(t_evals) != self.N_in:
+            raise DindError(_lib.ERR_SIZE_MISMATCH, f"expected {self.N_in} t_eval arrays")
+        for d, (dim, x) in enumerate(zip(self.interp_dims, t_evals)):
+            dim.set_t_eval(x)
+            self._h.set_t_eval(d, dim)
+        return self
+
     def set_u(self, u, flags=0):
         """Swap in a new `u` of the same shape (re-evaluation with the t_eval caches kept).
         flags=1 (DIND_FLAG_ASYNC) with a pinned host array: the upload is only queued — keep `u`
@@ -338,6 +353,13 @@ class NDInterpolation:
 
     def close(self):
         self._h.close()
+
+    def build_caches(self, *, grid=False, derivative_orders=None, flags=0):
+        """Build everything that depends on t_eval / u but not on the evaluation itself (axis tables of
+        eval_grid; component-fastest u, idx cache with FLAG_CACHED_IDX, cell-sorted plan with
+        FLAG_CELL_SORTED for eval_unstructured) — the constructors' set_eval_idx! / set_basis_function_eval!
+        step (src/interpolation_utils.jl:143-161, src/spline_utils.jl:164-191) as an explicit, timeable call."""
+        _lib.check(self._h.lib.dind_build_caches(self._h.h, 1 if grid else 0, _orders(derivative_orders, self.N_in), int(flags)))
 
     # -- evaluation --------------------------------------------------------------------------
     def _make_out(self, shape):

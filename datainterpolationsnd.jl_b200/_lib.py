@@ -31,6 +31,7 @@ SYMBOLS = [
     ("dind_eval_grid", _i, [_vp, _vp, _pint, _u]),
     ("dind_eval_unstructured_gradient", _i, [_vp, _vp, _u]),
     ("dind_eval_points", _i, [_vp, _vp, C.POINTER(_vp), _i64, _pint, _u]),
+    ("dind_build_caches", _i, [_vp, _i, _pint, _u]),
     ("dind_get_idx_eval", _i, [_vp, _i, _pi64]),
     ("dind_get_knots_all", _i, [_vp, _i, _vp, _pi64]),
     ("dind_get_basis_function_eval", _i, [_vp, _i, _vp]),

@@ -119,7 +119,7 @@ struct dind_interp_s {
     // cell-sorted plan for eval_unstructured (dind_plan.cu)
     bool plan_valid = false;
     int64_t plan_n = 0;
-    DevBuf plan_perm, plan_inv, plan_stage;
+    DevBuf plan_perm, plan_inv, plan_stage, plan_scratch;
     DevBuf plan_t[MAXN];
     // staging
     DevBuf out_stage[2];            // host `out`: device staging, double buffered for the pipelined (ASYNC) path
@@ -127,11 +127,20 @@ struct dind_interp_s {
     cudaStream_t copy_stream = nullptr;   // D2H of results, so that it overlaps the next step's H2D + kernel
     cudaEvent_t ev_kernel = nullptr, ev_d2h[2] = {nullptr, nullptr};
     DevBuf pts_stage[MAXN];
+    void* small_host = nullptr;     // pinned, device-mapped staging of the small-batch (latency) path of dind_eval_points
     std::string last_kernel = "none";
     int64_t launches = 0;
 };
 
 namespace {
+
+// internal: `out` is pinned host memory mapped into the device address space (small-batch path)
+constexpr unsigned FLAG_OUT_MAPPED = 1u << 31;
+// internal: stop after the caches / tables / plan are built (dind_build_caches)
+constexpr unsigned FLAG_BUILD_ONLY = 1u << 30;
+constexpr unsigned DIND_FLAG_PUBLIC_MASK = ~(FLAG_OUT_MAPPED | FLAG_BUILD_ONLY);
+constexpr size_t SMALL_BYTES = 64 << 10;    // staging size of the small-batch path
+constexpr int64_t SMALL_POINTS = 2048;
 
 bool is_device_ptr(const void* p) {
     cudaPointerAttributes a;
@@ -345,7 +354,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         if (D.kind == CONSTANT && orders[d] > 0) const_deriv = true;
         if (D.kind == LINEAR && orders[d] > 1) zero_result = true;
     }
-    const bool out_on_device = is_device_ptr(out);
+    const bool out_on_device = (flags & (FLAG_OUT_MAPPED | FLAG_BUILD_ONLY)) || is_device_ptr(out);
     // DIND_FLAG_ASYNC with a HOST `out` (pinned memory): the D2H copy is queued on the handle's copy
     // stream and the call returns; the caller reads `out` after dind_synchronize.  Two staging buffers
     // let the copy of step i overlap the H2D + kernel of step i + 1.
@@ -402,12 +411,10 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
             }
             size_t scratch_bytes = 0;
             CUDA_TRY(plan_sort_points<T>(P, nullptr, ts, nullptr, &scratch_bytes, h->stream));
-            DevBuf scratch;
-            CUDA_TRY(scratch.ensure(scratch_bytes));
-            cudaError_t pe = plan_sort_points<T>(P, (uint32_t*)h->plan_perm.p, ts, scratch.p, &scratch_bytes, h->stream);
-            if (pe == cudaSuccess) pe = cudaStreamSynchronize(h->stream);
-            scratch.release();
-            CUDA_TRY(pe);
+            // sort scratch (keys in/out, values in, CUB temp) stays with the handle: a new t_eval of the same
+            // size re-plans without cudaMalloc / cudaFree (which would also synchronise the device)
+            CUDA_TRY(h->plan_scratch.ensure(scratch_bytes));
+            CUDA_TRY(plan_sort_points<T>(P, (uint32_t*)h->plan_perm.p, ts, h->plan_scratch.p, &scratch_bytes, h->stream));
             CUDA_TRY(h->plan_inv.ensure((size_t)n_points * sizeof(uint32_t)));
             CUDA_TRY(plan_inverse((const uint32_t*)h->plan_perm.p, (uint32_t*)h->plan_inv.p, n_points, h->stream));
             h->launches += 3 + N;
@@ -435,11 +442,27 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         }
     }
 
+    const bool fast_ok = !(flags & DIND_FLAG_GENERIC) && !const_deriv && !zero_result;
+    // vector-valued u: gather from the component-fastest copy (rebuilt once per dind_set_u)
+    const bool use_aos = !gradient && fast_ok && !grid && aos_supported<T>(P) && !getenv("DIND_NO_AOS");
+    if (use_aos) {
+        if (!h->u_aos_valid) {
+            CUDA_TRY(h->u_aos.ensure((size_t)h->comp_stride * h->n_comp * sizeof(T)));
+            CUDA_TRY(launch_aos_repack<T>((const T*)h->d_u, (T*)h->u_aos.p, h->comp_stride, (int)h->n_comp, h->stream));
+            h->launches += 1;
+            h->u_aos_valid = true;
+        }
+        P.u_aos = (const T*)h->u_aos.p;
+    }
+    if (flags & FLAG_BUILD_ONLY) {
+        if (!(flags & DIND_FLAG_ASYNC)) CUDA_TRY(cudaStreamSynchronize(h->stream));
+        return DIND_OK;
+    }
+
     bool handled = false;
     cudaError_t err = cudaSuccess;
     const char* name = nullptr;
     int nlaunch = 0;
-    const bool fast_ok = !(flags & DIND_FLAG_GENERIC) && !const_deriv && !zero_result;
     if (gradient) {
         // one fused pass when the configuration is in the kernel's envelope, otherwise n_in + 1
         // ordinary evaluations into the n_in + 1 output slots
@@ -459,17 +482,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
             handled = true;
         }
     }
-    if (!handled && fast_ok && !grid && aos_supported<T>(P) && !getenv("DIND_NO_AOS")) {
-        // vector-valued u: gather from the component-fastest copy (rebuilt once per dind_set_u)
-        if (!h->u_aos_valid) {
-            CUDA_TRY(h->u_aos.ensure((size_t)h->comp_stride * h->n_comp * sizeof(T)));
-            CUDA_TRY(launch_aos_repack<T>((const T*)h->d_u, (T*)h->u_aos.p, h->comp_stride, (int)h->n_comp, h->stream));
-            h->launches += 1;
-            h->u_aos_valid = true;
-        }
-        P.u_aos = (const T*)h->u_aos.p;
-        handled = try_eval_fast_unstructured_aos<T>(P, h->stream, &name, &err, &nlaunch);
-    }
+    if (use_aos) handled = try_eval_fast_unstructured_aos<T>(P, h->stream, &name, &err, &nlaunch);
     if (fast_ok && !handled) {
         handled = grid ? try_eval_fast_grid<T>(P, h->stream, &name, &err, &nlaunch)
                        : try_eval_fast_unstructured<T>(P, h->stream, &name, &err, &nlaunch);
@@ -518,7 +531,7 @@ int eval_cached(dind_interp_s* h, void* out, const int* orders_in, bool grid, un
         for (int d = 1; d < h->n_in; ++d)
             if (n_eval[d] != n_eval[0])
                 return fail(DIND_ERR_SIZE_MISMATCH, "The t_eval of all interpolation dimensions must have the same length as the first dimension of out.");
-    if (!out) return fail(DIND_ERR_INVALID_ARGUMENT, "out is NULL");
+    if (!out && !(flags & FLAG_BUILD_ONLY)) return fail(DIND_ERR_INVALID_ARGUMENT, "out is NULL");
     return run_eval<T>(h, out, orders, grid, t_dev, n_eval, true, flags);
 }
 
@@ -533,9 +546,36 @@ int eval_points(dind_interp_s* h, void* out, const void* const* t, int64_t n, co
     if (!out || !t) return fail(DIND_ERR_INVALID_ARGUMENT, "out / t is NULL");
     const void* t_dev[MAXN];
     int64_t n_eval[MAXN];
+    bool all_host = !is_device_ptr(out);
     for (int d = 0; d < h->n_in; ++d) {
         if (!t[d]) return fail(DIND_ERR_INVALID_ARGUMENT, "t[%d] is NULL", d);
         n_eval[d] = n;
+        all_host = all_host && !is_device_ptr(t[d]);
+    }
+    flags &= ~(DIND_FLAG_CACHED_IDX | FLAG_OUT_MAPPED);
+    // Small-batch (latency) path — the single-point callable interp(t...) and ODE right-hand sides
+    // (SURVEY.md §8f-4): the coordinates and the results travel through one pinned, device-mapped
+    // staging buffer, so a call is ONE kernel launch + one stream synchronisation and no copy call.
+    const size_t t_bytes = (size_t)n * sizeof(T);
+    const size_t t_slot = (t_bytes + 15) & ~size_t(15);
+    const size_t out_bytes = (size_t)n * h->n_comp * sizeof(T);
+    if (all_host && n > 0 && n <= SMALL_POINTS && !(flags & DIND_FLAG_ASYNC) && t_slot * h->n_in + out_bytes <= SMALL_BYTES &&
+        !getenv("DIND_NO_SMALL")) {   // experiment knob: force the copy path
+        if (!h->small_host) CUDA_TRY(cudaHostAlloc(&h->small_host, SMALL_BYTES, cudaHostAllocMapped));
+        char* base = (char*)h->small_host;
+        for (int d = 0; d < h->n_in; ++d) {
+            memcpy(base + d * t_slot, t[d], t_bytes);
+            t_dev[d] = base + d * t_slot;
+        }
+        char* so = base + h->n_in * t_slot;
+        memcpy(so, out, out_bytes);   // Constant-with-derivative leaves vector outputs untouched (interpolation_methods.jl:49-55)
+        rc = run_eval<T>(h, so, orders, false, t_dev, n_eval, false, flags | DIND_FLAG_ASYNC | FLAG_OUT_MAPPED);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        memcpy(out, so, out_bytes);
+        return DIND_OK;
+    }
+    for (int d = 0; d < h->n_in; ++d) {
         if (is_device_ptr(t[d])) {
             t_dev[d] = t[d];
         } else {
@@ -544,7 +584,7 @@ int eval_points(dind_interp_s* h, void* out, const void* const* t, int64_t n, co
             t_dev[d] = h->pts_stage[d].p;
         }
     }
-    return run_eval<T>(h, out, orders, false, t_dev, n_eval, false, flags & ~DIND_FLAG_CACHED_IDX);
+    return run_eval<T>(h, out, orders, false, t_dev, n_eval, false, flags);
 }
 
 }  // namespace
@@ -596,10 +636,11 @@ int dind_destroy(dind_handle_t h) {
         h->pts_stage[d].release();
     }
     h->u_owned.release(); h->w_owned.release(); h->uw.release(); h->u_aos.release(); h->out_stage[0].release(); h->out_stage[1].release();
+    if (h->small_host) cudaFreeHost(h->small_host);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_kernel) cudaEventDestroy(h->ev_kernel);
     for (int i = 0; i < 2; ++i) if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
-    h->plan_perm.release(); h->plan_inv.release(); h->plan_stage.release();
+    h->plan_perm.release(); h->plan_inv.release(); h->plan_stage.release(); h->plan_scratch.release();
     for (int d = 0; d < MAXN; ++d) h->plan_t[d].release();
     delete h;
     return DIND_OK;
@@ -794,6 +835,7 @@ int dind_set_weights(dind_handle_t h, const void* weights, const int64_t* dims, 
 int dind_eval_unstructured(dind_handle_t h, void* out, const int* derivative_orders, unsigned flags) {
     int rc = check_handle(h);
     if (rc) return rc;
+    flags &= DIND_FLAG_PUBLIC_MASK;
     return h->dtype == DIND_F32 ? eval_cached<float>(h, out, derivative_orders, false, flags)
                                 : eval_cached<double>(h, out, derivative_orders, false, flags);
 }
@@ -801,6 +843,7 @@ int dind_eval_unstructured(dind_handle_t h, void* out, const int* derivative_ord
 int dind_eval_grid(dind_handle_t h, void* out, const int* derivative_orders, unsigned flags) {
     int rc = check_handle(h);
     if (rc) return rc;
+    flags &= DIND_FLAG_PUBLIC_MASK;
     return h->dtype == DIND_F32 ? eval_cached<float>(h, out, derivative_orders, true, flags)
                                 : eval_cached<double>(h, out, derivative_orders, true, flags);
 }
@@ -835,7 +878,16 @@ int eval_gradient(dind_interp_s* h, void* out, unsigned flags) {
 int dind_eval_unstructured_gradient(dind_handle_t h, void* out, unsigned flags) {
     int rc = check_handle(h);
     if (rc) return rc;
+    flags &= DIND_FLAG_PUBLIC_MASK;
     return h->dtype == DIND_F32 ? eval_gradient<float>(h, out, flags) : eval_gradient<double>(h, out, flags);
+}
+
+int dind_build_caches(dind_handle_t h, int grid, const int* derivative_orders, unsigned flags) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    flags = (flags & DIND_FLAG_PUBLIC_MASK) | FLAG_BUILD_ONLY;
+    return h->dtype == DIND_F32 ? eval_cached<float>(h, nullptr, derivative_orders, grid != 0, flags)
+                                : eval_cached<double>(h, nullptr, derivative_orders, grid != 0, flags);
 }
 
 int dind_eval_points(dind_handle_t h, void* out, const void* const* t, int64_t n, const int* derivative_orders,

@@ -263,4 +263,15 @@ __device__ __forceinline__ void dim_stencil(const DimParams<T>& D, T x, int orde
     }
 }
 
+// First stencil node only (the i0 of dim_stencil, without the weights): key of the cell-sorted plan.
+template <typename T>
+__device__ __forceinline__ int dim_first_node(const DimParams<T>& D, T x) {
+    const typename KeyOf<T>::type kx = to_key(x);
+    const int n = D.n_knots;
+    if (D.kind == LINEAR) return clampi(dim_count<T, false>(D, x, kx), 1, n - 1) - 1;
+    if (D.kind == CONSTANT) return (x >= D.knots[n - 1]) ? n - 1 : clampi(dim_count<T, true>(D, x, kx), 1, n - 1) - 1;
+    const int p = D.degree;
+    return clampi(dim_count<T, true>(D, x, kx), p + 1, n - p - 1) - p - 1;
+}
+
 }  // namespace dind

@@ -27,11 +27,7 @@ __global__ void __launch_bounds__(BLOCK) plan_key_kernel(const __grid_constant__
     int64_t base = 0;
     for (int d = 0; d < P.n_in; ++d) {
         const DimParams<T>& D = P.dim[d];
-        T w[MAXW];
-        int i0, idx1;
-        bool on_knot;
-        dim_stencil<T>(D, D.t_eval[k], 0, 0, i0, w, on_knot, idx1);
-        base += (int64_t)i0 * D.u_stride;
+        base += (int64_t)dim_first_node<T>(D, __ldcs(D.t_eval + k)) * D.u_stride;
     }
     keys[k] = (uint32_t)base;
     vals[k] = (uint32_t)k;

@@ -16,7 +16,7 @@ using Libdl
 
 export NDInterpolation, LinearInterpolationDimension, ConstantInterpolationDimension,
     BSplineInterpolationDimension, NURBSWeights, EmptyCache,
-    eval_unstructured, eval_unstructured!, eval_grid, eval_grid!, eval_unstructured_gradient!
+    eval_unstructured, eval_unstructured!, eval_grid, eval_grid!, eval_unstructured_gradient!, build_caches!
 
 # a const String: `ccall((:sym, libdind), ...)` needs a constant library expression
 const libdind = get(ENV, "LIBDIND", joinpath(@__DIR__, "..", "..", "..", "libdind.so"))
@@ -205,6 +205,15 @@ function eval_unstructured_gradient!(out::AbstractArray{T}, itp::NDInterpolation
     GC.@preserve out check(ccall((:dind_eval_unstructured_gradient, libdind), Cint,
         (Ptr{Cvoid}, Ptr{Cvoid}, Cuint), itp.handle, out, 0))
     return out
+end
+
+# ---- explicit cache construction (dind_build_caches): the constructors' set_eval_idx! step, timeable --------
+function build_caches!(itp::NDInterpolation{N_in}; grid::Bool = false,
+        derivative_orders::NTuple{N_in, <:Integer} = ntuple(_ -> 0, N_in), flags::Integer = 0) where {N_in}
+    o = orders_arg(derivative_orders)
+    GC.@preserve o check(ccall((:dind_build_caches, libdind), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Cint}, Cuint), itp.handle, grid ? 1 : 0, o, flags))
+    return itp
 end
 
 # ---- single point calls (src/DataInterpolationsND.jl:73-100) through dind_eval_points with n = 1 --------

@@ -138,7 +138,10 @@ int dind_eval_unstructured(dind_handle_t handle, void* out, const int* derivativ
 int dind_eval_grid(dind_handle_t handle, void* out, const int* derivative_orders, unsigned flags);
 /* Batched form of the uncached in-place call interp(out, t...; derivative_orders) —
  * src/DataInterpolationsND.jl:85-94: t[d] points to n values for dimension d (all host or all
- * device); out is (n, out...).  Does not touch the handle's t_eval. */
+ * device); out is (n, out...).  Does not touch the handle's t_eval.  Small all-host batches
+ * (n <= 2048, <= 64 KB) take a latency path: coordinates and results travel through one pinned,
+ * device-mapped staging buffer — one kernel launch + one stream synchronisation, no copy calls
+ * (the single-point callable interp(t...), src/DataInterpolationsND.jl:73-83). */
 int dind_eval_points(dind_handle_t handle, void* out, const void* const* t, int64_t n,
                      const int* derivative_orders, unsigned flags);
 
@@ -150,6 +153,17 @@ int dind_eval_points(dind_handle_t handle, void* out, const void* const* t, int6
  * Linear and BSpline dimensions (BSpline needs max_derivative_order_eval >= 1); Constant dimensions
  * and NURBS weights return DIND_ERR_UNSUPPORTED.  Honours DIND_FLAG_ASYNC / DIND_FLAG_CELL_SORTED. */
 int dind_eval_unstructured_gradient(dind_handle_t handle, void* out, unsigned flags);
+
+/* Cache construction as an explicit, timeable step — the work the reference's
+ * constructors do in set_eval_idx! (src/interpolation_utils.jl:143-161) and
+ * set_basis_function_eval! (src/spline_utils.jl:164-191), i.e. everything that depends on
+ * t_eval / u but not on the evaluation itself, so that the first evaluation does not pay for it:
+ *   grid != 0: the per-axis index/weight tables eval_grid uses for `derivative_orders`;
+ *   grid == 0: the component-fastest copy of u (vector-valued u), the per-point index cache with
+ *              DIND_FLAG_CACHED_IDX, the cell-sorted plan with DIND_FLAG_CELL_SORTED.
+ * Needs dind_set_dim, dind_set_t_eval and dind_set_u.  Evaluations build whatever is missing
+ * lazily, so calling this is optional.  Honours DIND_FLAG_ASYNC. */
+int dind_build_caches(dind_handle_t handle, int grid, const int* derivative_orders, unsigned flags);
 
 /* ---- introspection (parity tests; fields the reference exposes on its structs) ---------- */
 /* idx_eval, 1-based Int64 exactly as the reference stores it (src/interpolation_dimensions.jl:38). */

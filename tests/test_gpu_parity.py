@@ -332,6 +332,9 @@ def test_validation_errors(D):
     itp2.close()
 
 
+CELL_SORTED = 16
+
+
 def test_single_point_in_place_and_eval_points(D):   # src/DataInterpolationsND.jl:85-94
     rng = np.random.default_rng(2)
     t1, t2 = H.knots(rng, 6), H.knots(rng, 7)
@@ -347,6 +350,69 @@ def test_single_point_in_place_and_eval_points(D):   # src/DataInterpolationsND.
     got = itp.eval_points(xs, derivative_orders=(1, 0))
     H.assert_close(got, O.evaluate(["linear"] * 2, [t1, t2], u, xs, derivative_orders=(1, 0)), np.float64)
     itp.close()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [1, 2, 31, 2048, 2049, 5000])
+def test_eval_points_small_batch_path_equals_copy_path(D, dtype, n):
+    """dind_eval_points takes a pinned, device-mapped staging path for small all-host batches
+    (n <= 2048); results must be bit-identical to the copy path and to the cached evaluation."""
+    rng = np.random.default_rng(40 + n)
+    ts = [H.knots(rng, 9, dtype), H.knots(rng, 8, dtype), H.knots(rng, 7, dtype)]
+    u = rng.random((10, 9, 8, 2)).astype(dtype)
+    xs = [rng.uniform(t[0], t[-1], n).astype(dtype) for t in ts]
+    dims = tuple(D.BSplineInterpolationDimension(t, 2, t_eval=x, max_derivative_order_eval=1) for t, x in zip(ts, xs))
+    itp = D.NDInterpolation(u, dims)
+    for orders in [(0, 0, 0), (1, 0, 1)]:
+        got = itp.eval_points(xs, derivative_orders=orders)                      # small path for n <= 2048
+        cached = D.eval_unstructured(itp, derivative_orders=orders)
+        np.testing.assert_array_equal(got, cached)
+        import torch
+        dev = itp.eval_points([torch.from_numpy(x).cuda() for x in xs], derivative_orders=orders)   # device pointers: no staging
+        np.testing.assert_array_equal(dev.cpu().numpy(), cached)
+        ref = O.evaluate(["bspline"] * 3, ts, u, xs, degrees=[2] * 3, derivative_orders=orders)
+        H.assert_close(got, ref, dtype)
+    itp.close()
+
+
+def test_eval_points_small_batch_keeps_untouched_semantics(D):   # src/interpolation_methods.jl:49-55
+    t = np.array([0.0, 1.0, 2.0, 3.0])
+    u = np.arange(8.0).reshape(4, 2)
+    itp = D.NDInterpolation(u, D.ConstantInterpolationDimension(t))
+    out = np.full((3, 2), 7.0, order="F")
+    itp.eval_points([np.array([0.5, 1.0, 2.5])], out=out, derivative_orders=(1,))
+    assert np.all(out[[0, 2]] == 7.0) and np.all(np.isnan(out[1]))     # off the knots: untouched; on a knot: NaN
+    one = np.full(2, 5.0)
+    itp(0.5, out=one, derivative_orders=(1,))
+    assert np.all(one == 5.0)
+    itp.close()
+
+
+def test_build_caches_is_optional_and_idempotent(D):
+    rng = np.random.default_rng(77)
+    ts = [H.knots(rng, 12), H.knots(rng, 10)]
+    u = rng.random((12, 10, 3))
+    xs = [rng.uniform(t[0] - 0.3, t[-1] + 0.3, 4000) for t in ts]
+    mk = lambda: D.NDInterpolation(u, tuple(D.LinearInterpolationDimension(t, t_eval=x) for t, x in zip(ts, xs)))
+    a, b = mk(), mk()
+    n0 = b.launch_count
+    b.build_caches(flags=CELL_SORTED | 4)          # plan + idx cache + component-fastest u, no evaluation
+    n1 = b.launch_count
+    assert n1 > n0
+    b.build_caches(flags=CELL_SORTED | 4)          # nothing left to build
+    assert b.launch_count == n1
+    assert b.plan_permutation().shape == (4000,)
+    np.testing.assert_array_equal(D.eval_unstructured(b, flags=CELL_SORTED), D.eval_unstructured(a))
+    assert b.launch_count - n1 == 2                # evaluation kernel + un-permutation only
+    g = D.NDInterpolation(rng.random((12, 10)), tuple(D.LinearInterpolationDimension(t, t_eval=np.sort(x[:50])) for t, x in zip(ts, xs)))
+    g.build_caches(grid=True, derivative_orders=(1, 0))
+    n2 = g.launch_count
+    D.eval_grid(g, derivative_orders=(1, 0))
+    assert g.launch_count - n2 == 1                # tables were ready
+    with pytest.raises(AssertionError):
+        D.NDInterpolation(u, tuple(D.LinearInterpolationDimension(t) for t in ts)).build_caches(derivative_orders=(0, -1))
+    for i in (a, b, g):
+        i.close()
 
 
 def test_empty_and_single_point_batches(D):
@@ -383,7 +449,6 @@ def test_device_tensors_zero_copy_and_new_u(D):
 
 
 # ---- cell-sorted plan: same numbers, original output positions ---------------------------------------
-CELL_SORTED = 16
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
