@@ -140,8 +140,20 @@ struct EvalParams {
     int32_t const_deriv;   // some Constant dimension has derivative order > 0
     int32_t zero_result;   // Linear with order > 1 somewhere: result is identically zero
     int32_t use_cached_idx;
-    const uint32_t* perm;  // cell-sorted plan: point k of the (sorted) t_eval arrays is original point perm[k]; null = identity
+    const uint32_t* perm;  // cell-sorted plan: output position of point k of the (sorted) t_eval arrays; null = identity
+    int32_t staged_records;  // out is the plan's staging buffer: component-fastest records of out_point_stride
+                             // elements, padded and aligned as plan_record_stride() says (vector stores allowed)
 };
+
+// Elements per staging record for ct result values of esz bytes: records of up to 32 bytes are padded to
+// 8 / 16 / 32 bytes so that one record is one aligned vector store and never straddles a 32-byte sector.
+__host__ __device__ inline int plan_record_stride(int ct, int esz) {
+    const int bytes = ct * esz;
+    if (bytes <= 8) return ct;
+    if (bytes <= 16) return 16 / esz;
+    if (bytes <= 32) return 32 / esz;
+    return ((bytes + 15) / 16) * (16 / esz);
+}
 
 // count of knots < x (LE = false: searchsortedfirst - 1) or <= x (LE = true: searchsortedlast) in
 // Julia's isless order, through the bucket table when the dimension has one.
@@ -260,6 +272,27 @@ __device__ __forceinline__ void dim_stencil(const DimParams<T>& D, T x, int orde
         idx1 = idx;
         i0 = idx - p - 1;                                                   // :87-89
         bspline_basis_rt<T>(D.knots, D.recip, n, p, idx - 1, x, order, w);
+    }
+}
+
+// One staging record (see plan_record_stride) with the widest store it allows; 32-byte records leave as
+// one full-sector 256-bit store (STG.256, sm_100).
+template <typename T, int C>
+__device__ __forceinline__ void store_record(T* dst, const T (&v)[C]) {
+    constexpr int BYTES = C * (int)sizeof(T);
+    if constexpr (sizeof(T) == 4 && C == 2) {
+        *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+    } else if constexpr (sizeof(T) == 4 && BYTES <= 16) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], C > 3 ? v[C - 1] : 0.f);
+    } else if constexpr (sizeof(T) == 8 && C == 2) {
+        *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+    } else if constexpr (sizeof(T) == 8 && BYTES <= 32) {
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(v[0]), "d"(v[1]), "d"(v[2]),
+                     "d"(C > 3 ? v[C - 1] : 0.0)
+                     : "memory");
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) dst[c] = v[c];
     }
 }
 

@@ -110,6 +110,10 @@ __global__ void __launch_bounds__(ABLOCK) unstructured_aos_kernel(const __grid_c
     }
     const int64_t ko = P.perm ? (int64_t)__ldcs(P.perm + k) : k;
     const Vec<T, C> acc = ContractV<T, N - 1, W, C>::run(P.u_aos + base * C, w, stride);
+    if (P.staged_records) {   // cell-sorted plan: one aligned record per point
+        store_record<T, C>(P.out + ko * P.out_point_stride, acc.v);
+        return;
+    }
 #pragma unroll
     for (int c = 0; c < C; ++c) __stcs(P.out + (int64_t)c * P.out_comp_stride + ko * P.out_point_stride, acc.v[c]);
 }

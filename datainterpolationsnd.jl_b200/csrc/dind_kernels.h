@@ -37,10 +37,12 @@ template <typename T> bool try_eval_fast_unstructured_aos(const EvalParams<T>& P
 template <typename T> bool try_eval_fast_gradient(const EvalParams<T>& P, cudaStream_t s, const char** name,
                                                   cudaError_t* err, int* launches);
 
-// inv[perm[k]] = k, and the gather that brings plan-ordered, component-fastest staged results back to
-// the reference layout out[(point, component)].
-cudaError_t plan_inverse(const uint32_t* perm, uint32_t* inv, int64_t n, cudaStream_t s);
-template <typename T> cudaError_t plan_unpermute(const T* staged, const uint32_t* inv, T* out, int64_t n, int ct, cudaStream_t s);
+// Two-level un-permutation (dind_plan.cu): slot2[k] = staging slot of plan position k (slots ordered by
+// the window of the destination), dest2[j] = destination of slot j; plan_unbucket copies slot j home.
+cudaError_t plan_bucket_schedule(const uint32_t* perm, uint32_t* slot2, uint32_t* dest2, int64_t n, void* scratch,
+                                 size_t* scratch_bytes, cudaStream_t s);
+constexpr int PLAN_WINDOW_SHIFT = 11;   // windows of 2048 original points
+template <typename T> cudaError_t plan_unbucket(const T* staged, const uint32_t* dest2, T* out, int64_t n, int ct, int rec_stride, cudaStream_t s);
 
 // Specialised kernels.  Return true when they handled the evaluation (err holds the launch
 // status), false when the configuration is outside their envelope.

@@ -40,36 +40,123 @@ __global__ void __launch_bounds__(BLOCK) plan_gather_kernel(const T* __restrict_
     if (k < n) dst[k] = src[perm[k]];
 }
 
-__global__ void __launch_bounds__(BLOCK) plan_inverse_kernel(const uint32_t* __restrict__ perm, uint32_t* __restrict__ inv, int64_t n) {
+// ---- two-level un-permutation ------------------------------------------------------------------
+// Bringing plan-ordered results back to the caller's order is a random permutation over the whole
+// output (config 3: 480 MB, config 5: 1.6 GB): as one gather it runs at DRAM-sector/TLB speed.
+// Instead the original index space is cut into windows of 2^shift points; the evaluation kernel
+// writes the result of plan position k to staging slot slot2[k], where the slots are ordered by
+// (window of the destination, k) — a few hundred sequential write streams that L2 write-combines —
+// and a second pass copies slot j to its destination dest2[j], which lies inside a window small
+// enough to be assembled in shared memory (plan_unbucket_kernel).
+__global__ void __launch_bounds__(BLOCK) bucket_key_kernel(const uint32_t* __restrict__ perm, uint32_t* __restrict__ keys,
+                                                           uint32_t* __restrict__ vals, int64_t n, int shift) {
     const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-    if (k < n) inv[perm[k]] = (uint32_t)k;
+    if (k >= n) return;
+    keys[k] = __ldcs(perm + k) >> shift;
+    vals[k] = (uint32_t)k;
 }
 
-// out[i + cc * n] = staged[inv[i] * ct + cc]: one random (ct * sizeof(T))-byte read per point, coalesced
-// writes — instead of ct random read-modify-write sector accesses per point for a direct scatter.
+__global__ void __launch_bounds__(BLOCK) bucket_slots_kernel(const uint32_t* __restrict__ order2, const uint32_t* __restrict__ perm,
+                                                             uint32_t* __restrict__ slot2, uint32_t* __restrict__ dest2, int64_t n) {
+    const int64_t j = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t k = __ldcs(order2 + j);
+    slot2[k] = (uint32_t)j;
+    dest2[j] = perm[k];
+}
+
+// Second pass: one CTA per window of UNB_W original points.  The window's records are exactly the staging
+// slots [w * UNB_W, w * UNB_W + size) (the map is a permutation, so every window receives as many records
+// as it has points); they are read in order, dropped at their place in a shared-memory image of the
+// window (component-major), and the image leaves with fully coalesced streaming stores.
+constexpr int UNB_W = 1 << PLAN_WINDOW_SHIFT;
+constexpr int UNB_BLOCK = 512;
+
 template <typename T>
-__global__ void __launch_bounds__(BLOCK) plan_unpermute_kernel(const T* __restrict__ staged, const uint32_t* __restrict__ inv,
-                                                               T* __restrict__ out, int64_t n, int ct) {
-    const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-    if (i >= n) return;
-    const T* src = staged + (int64_t)__ldcs(inv + i) * ct;
-    for (int cc = 0; cc < ct; ++cc) __stcs(out + i + (int64_t)cc * n, __ldcs(src + cc));
+__global__ void __launch_bounds__(UNB_BLOCK) plan_unbucket_kernel(const T* __restrict__ staged, const uint32_t* __restrict__ dest2,
+                                                                  T* __restrict__ out, int64_t n, int ct, int rec_stride, int cg) {
+    extern __shared__ __align__(16) unsigned char unb_smem[];
+    T* sm = reinterpret_cast<T*>(unb_smem);   // [cg][UNB_W]
+    const int64_t w0 = (int64_t)blockIdx.x * UNB_W;
+    const int wn = (int)(n - w0 < UNB_W ? n - w0 : UNB_W);
+    for (int c0 = 0; c0 < ct; c0 += cg) {
+        const int cn = ct - c0 < cg ? ct - c0 : cg;
+        for (int r = threadIdx.x; r < wn; r += UNB_BLOCK) {
+            const int li = (int)(__ldcs(dest2 + w0 + r) - (uint32_t)w0);
+            const T* src = staged + (w0 + r) * rec_stride + c0;
+            if (sizeof(T) == 8 && rec_stride == 4 && cn == ct) {          // 32-byte record: two 16-byte loads
+                const double2 a = __ldcs(reinterpret_cast<const double2*>(src));
+                const double2 b = __ldcs(reinterpret_cast<const double2*>(src) + 1);
+                sm[li] = (T)a.x;
+                if (ct > 1) sm[UNB_W + li] = (T)a.y;
+                if (ct > 2) sm[2 * UNB_W + li] = (T)b.x;
+                if (ct > 3) sm[3 * UNB_W + li] = (T)b.y;
+            } else if (sizeof(T) == 4 && rec_stride == 4 && cn == ct) {   // 16-byte record
+                const float4 a = __ldcs(reinterpret_cast<const float4*>(src));
+                sm[li] = (T)a.x;
+                if (ct > 1) sm[UNB_W + li] = (T)a.y;
+                if (ct > 2) sm[2 * UNB_W + li] = (T)a.z;
+                if (ct > 3) sm[3 * UNB_W + li] = (T)a.w;
+            } else {
+                for (int cc = 0; cc < cn; ++cc) sm[cc * UNB_W + li] = __ldcs(src + cc);
+            }
+        }
+        __syncthreads();
+        for (int cc = 0; cc < cn; ++cc)
+            for (int li = threadIdx.x; li < wn; li += UNB_BLOCK) __stcs(out + w0 + li + (int64_t)(c0 + cc) * n, sm[cc * UNB_W + li]);
+        __syncthreads();
+    }
 }
 
 }  // namespace
 
-cudaError_t plan_inverse(const uint32_t* perm, uint32_t* inv, int64_t n, cudaStream_t s) {
-    plan_inverse_kernel<<<(unsigned)((n + BLOCK - 1) / BLOCK), BLOCK, 0, s>>>(perm, inv, n);
+cudaError_t plan_bucket_schedule(const uint32_t* perm, uint32_t* slot2, uint32_t* dest2, int64_t n, void* scratch,
+                                 size_t* scratch_bytes, cudaStream_t s) {
+    const int shift = PLAN_WINDOW_SHIFT;
+    int end_bit = 1;
+    while (end_bit < 32 && (1LL << end_bit) <= ((n - 1) >> shift)) ++end_bit;
+    size_t cub_bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, end_bit, s);
+    if (e != cudaSuccess) return e;
+    const size_t arr = ((size_t)n * sizeof(uint32_t) + 255) & ~(size_t)255;
+    const size_t need = 4 * arr + cub_bytes;   // keys in/out, values in/out (+ CUB temp)
+    if (!scratch) {
+        *scratch_bytes = need;
+        return cudaSuccess;
+    }
+    if (*scratch_bytes < need) return cudaErrorInvalidValue;
+    char* base = (char*)scratch;
+    uint32_t* keys_in = (uint32_t*)base;
+    uint32_t* keys_out = (uint32_t*)(base + arr);
+    uint32_t* vals_in = (uint32_t*)(base + 2 * arr);
+    uint32_t* order2 = (uint32_t*)(base + 3 * arr);
+    void* cub_tmp = base + 4 * arr;
+    const unsigned nb = (unsigned)((n + BLOCK - 1) / BLOCK);
+    bucket_key_kernel<<<nb, BLOCK, 0, s>>>(perm, keys_in, vals_in, n, shift);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    e = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, keys_out, vals_in, order2, n, 0, end_bit, s);   // stable
+    if (e != cudaSuccess) return e;
+    bucket_slots_kernel<<<nb, BLOCK, 0, s>>>(order2, perm, slot2, dest2, n);
     return cudaGetLastError();
 }
 
 template <typename T>
-cudaError_t plan_unpermute(const T* staged, const uint32_t* inv, T* out, int64_t n, int ct, cudaStream_t s) {
-    plan_unpermute_kernel<T><<<(unsigned)((n + BLOCK - 1) / BLOCK), BLOCK, 0, s>>>(staged, inv, out, n, ct);
+cudaError_t plan_unbucket(const T* staged, const uint32_t* dest2, T* out, int64_t n, int ct, int rec_stride, cudaStream_t s) {
+    const int cg_max = (96 * 1024) / (UNB_W * (int)sizeof(T));   // components per round: <= 96 KB of shared memory
+    const int cg = ct < cg_max ? ct : cg_max;
+    const size_t smem = (size_t)cg * UNB_W * sizeof(T);
+    static bool attr_set = false;   // per template instance
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(plan_unbucket_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    plan_unbucket_kernel<T><<<(unsigned)((n + UNB_W - 1) / UNB_W), UNB_BLOCK, smem, s>>>(staged, dest2, out, n, ct, rec_stride, cg);
     return cudaGetLastError();
 }
-template cudaError_t plan_unpermute<float>(const float*, const uint32_t*, float*, int64_t, int, cudaStream_t);
-template cudaError_t plan_unpermute<double>(const double*, const uint32_t*, double*, int64_t, int, cudaStream_t);
+template cudaError_t plan_unbucket<float>(const float*, const uint32_t*, float*, int64_t, int, int, cudaStream_t);
+template cudaError_t plan_unbucket<double>(const double*, const uint32_t*, double*, int64_t, int, int, cudaStream_t);
 
 template <typename T>
 cudaError_t plan_sort_points(const EvalParams<T>& P, uint32_t* perm, T* const* t_sorted, void* scratch,
