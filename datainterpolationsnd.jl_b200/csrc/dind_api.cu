@@ -428,6 +428,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
             P.dim[d].idx_eval = nullptr;
         }
         P.use_cached_idx = 0;
+        P.coherent_points = 1;
         P.perm = (flags & DIND_FLAG_PLAN_ORDER) ? nullptr : (const uint32_t*)h->plan_perm.p;
         // Results go back to their original positions in two levels (dind_plan.cu): the kernel writes each
         // result as one aligned record to a staging slot ordered by the 2048-point window of its destination,
@@ -464,10 +465,10 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
 
     const bool fast_ok = !(flags & DIND_FLAG_GENERIC) && !const_deriv && !zero_result;
     // vector-valued u: gather from the component-fastest copy (rebuilt once per dind_set_u)
-    const bool use_aos = !gradient && fast_ok && !grid && aos_supported<T>(P) && !getenv("DIND_NO_AOS");
+    const bool use_aos = fast_ok && !grid && aos_supported<T>(P) && !getenv("DIND_NO_AOS");
     if (use_aos) {
         if (!h->u_aos_valid) {
-            CUDA_TRY(h->u_aos.ensure((size_t)h->comp_stride * h->n_comp * sizeof(T)));
+            CUDA_TRY(h->u_aos.ensure((size_t)h->comp_stride * aos_node_stride((int)h->n_comp) * sizeof(T)));
             CUDA_TRY(launch_aos_repack<T>((const T*)h->d_u, (T*)h->u_aos.p, h->comp_stride, (int)h->n_comp, h->stream));
             h->launches += 1;
             h->u_aos_valid = true;
@@ -502,7 +503,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
             handled = true;
         }
     }
-    if (use_aos) handled = try_eval_fast_unstructured_aos<T>(P, h->stream, &name, &err, &nlaunch);
+    if (use_aos && !handled) handled = try_eval_fast_unstructured_aos<T>(P, h->stream, &name, &err, &nlaunch);
     if (fast_ok && !handled) {
         handled = grid ? try_eval_fast_grid<T>(P, h->stream, &name, &err, &nlaunch)
                        : try_eval_fast_unstructured<T>(P, h->stream, &name, &err, &nlaunch);

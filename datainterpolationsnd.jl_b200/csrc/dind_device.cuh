@@ -141,6 +141,7 @@ struct EvalParams {
     int32_t zero_result;   // Linear with order > 1 somewhere: result is identically zero
     int32_t use_cached_idx;
     const uint32_t* perm;  // cell-sorted plan: output position of point k of the (sorted) t_eval arrays; null = identity
+    int32_t coherent_points; // neighbouring points share their stencil (cell-sorted plan): prefer narrow, broadcast loads
     int32_t staged_records;  // out is the plan's staging buffer: component-fastest records of out_point_stride
                              // elements, padded and aligned as plan_record_stride() says (vector stores allowed)
 };
@@ -280,6 +281,7 @@ __device__ __forceinline__ void dim_stencil(const DimParams<T>& D, T x, int orde
 template <typename T, int C>
 __device__ __forceinline__ void store_record(T* dst, const T (&v)[C]) {
     constexpr int BYTES = C * (int)sizeof(T);
+    constexpr int PER16 = 16 / (int)sizeof(T);
     if constexpr (sizeof(T) == 4 && C == 2) {
         *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
     } else if constexpr (sizeof(T) == 4 && BYTES <= 16) {
@@ -290,10 +292,58 @@ __device__ __forceinline__ void store_record(T* dst, const T (&v)[C]) {
         asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(v[0]), "d"(v[1]), "d"(v[2]),
                      "d"(C > 3 ? v[C - 1] : 0.0)
                      : "memory");
+    } else if constexpr (sizeof(T) == 8 && BYTES % 32 == 0) {
+#pragma unroll
+        for (int i = 0; i < C; i += 4)
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "d"(v[i]), "d"(v[i + 1]), "d"(v[i + 2]),
+                         "d"(v[i + 3])
+                         : "memory");
+    } else if constexpr (BYTES > 16) {   // 16-byte chunks, scalar tail (the record stride is a multiple of 16 bytes)
+#pragma unroll
+        for (int i = 0; i + PER16 <= C; i += PER16) {
+            if constexpr (sizeof(T) == 8) *reinterpret_cast<double2*>(dst + i) = make_double2(v[i], v[i + 1]);
+            else *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+#pragma unroll
+        for (int i = C - C % PER16; i < C; ++i) dst[i] = v[i];
     } else {
 #pragma unroll
         for (int c = 0; c < C; ++c) dst[c] = v[c];
     }
+}
+
+// ---- component-fastest ("AoS") copy of u: node i holds its n_comp values in aos_node_stride(n_comp)
+// consecutive elements (dind_fast_unstructured_aos.cu, dind_fast_gradient.cu)
+template <typename T, int C>
+struct Vec {
+    T v[C];
+};
+
+// all components of one node (aos_node_stride(C) elements, 8 / 16 / 32 bytes, aligned): ONE vector load —
+// 32-byte nodes (3 or 4 doubles) through the 256-bit load of sm_100 (LDG.E.256)
+// — unless the points are known to be warp-coherent (cell-sorted plan): lanes then read the SAME node, a
+// 64-bit load of one address is one L1 wavefront and the 256-bit load is slower (measured, config 3).
+template <typename T, int C, bool WIDE>
+__device__ __forceinline__ Vec<T, C> load_node(const T* __restrict__ p) {
+    constexpr int BYTES = (int)sizeof(T) * (C == 3 ? 4 : C);
+    static_assert(BYTES == 8 || BYTES == 16 || BYTES == 32, "node size");
+    Vec<T, C> r;
+    if constexpr (BYTES == 32 && !WIDE) {   // (a 16-byte + 8-byte split is slower than three 8-byte loads here, measured)
+#pragma unroll
+        for (int c = 0; c < C; ++c) r.v[c] = __ldg(p + c);
+    } else if constexpr (BYTES == 16) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+        memcpy(&r, &q, sizeof(T) * C);
+    } else if constexpr (BYTES == 8) {
+        const float2 q = __ldg(reinterpret_cast<const float2*>(p));
+        memcpy(&r, &q, 8);
+    } else {
+        double q[4];
+        asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(q[0]), "=d"(q[1]), "=d"(q[2]), "=d"(q[3]) : "l"(p));
+#pragma unroll
+        for (int c = 0; c < C; ++c) r.v[c] = (T)q[c];
+    }
+    return r;
 }
 
 // First stencil node only (the i0 of dim_stencil, without the weights): key of the cell-sorted plan.

@@ -55,6 +55,46 @@ struct ContractG<T, 0, W> {
     }
 };
 
+// The same contraction over the component-fastest copy of u: every node is ONE vector load for all C
+// components (instead of C gathers from C distant volumes); accumulator (slot j, component c) = g[j * C + c].
+template <typename T, int D, int W, int C, bool WIDE>
+struct ContractGV {
+    static __device__ __forceinline__ GVec<T, (D + 2) * C> run(const T* __restrict__ p, const T (&w)[MAXN][W],
+                                                               const T (&dw)[MAXN][W], const int (&stride)[MAXN]) {
+        GVec<T, (D + 2) * C> r;
+#pragma unroll
+        for (int j = 0; j < (D + 2) * C; ++j) r.g[j] = T(0);
+#pragma unroll
+        for (int a = 0; a < W; ++a) {
+            const GVec<T, (D + 1) * C> sub = ContractGV<T, D - 1, W, C, WIDE>::run(p + a * stride[D], w, dw, stride);
+#pragma unroll
+            for (int j = 0; j < (D + 1) * C; ++j) r.g[j] = fma(w[D][a], sub.g[j], r.g[j]);
+#pragma unroll
+            for (int c = 0; c < C; ++c) r.g[(D + 1) * C + c] = fma(dw[D][a], sub.g[c], r.g[(D + 1) * C + c]);
+        }
+        return r;
+    }
+};
+template <typename T, int W, int C, bool WIDE>
+struct ContractGV<T, 0, W, C, WIDE> {
+    static __device__ __forceinline__ GVec<T, 2 * C> run(const T* __restrict__ p, const T (&w)[MAXN][W], const T (&dw)[MAXN][W],
+                                                         const int (&)[MAXN]) {
+        GVec<T, 2 * C> r;
+#pragma unroll
+        for (int j = 0; j < 2 * C; ++j) r.g[j] = T(0);
+#pragma unroll
+        for (int a = 0; a < W; ++a) {
+            const Vec<T, C> v = load_node<T, C, WIDE>(p + a * (C == 3 ? 4 : C));
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                r.g[c] = fma(w[0][a], v.v[c], r.g[c]);
+                r.g[C + c] = fma(dw[0][a], v.v[c], r.g[C + c]);
+            }
+        }
+        return r;
+    }
+};
+
 // order-0 and order-1 stencil weights of one dimension (compile-time width)
 template <typename T, int W>
 __device__ __forceinline__ int stencil_w_dw(const DimParams<T>& D, T x, T (&w)[W], T (&dw)[W]) {
@@ -98,9 +138,59 @@ __global__ void __launch_bounds__(GBLOCK) unstructured_gradient_kernel(const __g
     }
 }
 
+template <typename T, int N, int W, int C, bool WIDE>
+__global__ void __launch_bounds__(GBLOCK, 2) unstructured_gradient_aos_kernel(const __grid_constant__ EvalParams<T> P) {
+    const int64_t k = (int64_t)blockIdx.x * GBLOCK + threadIdx.x;
+    if (k >= P.n_points) return;
+    constexpr int S = C == 3 ? 4 : C;   // aos_node_stride(C)
+    T w[MAXN][W], dw[MAXN][W];
+    int stride[MAXN];
+    int64_t base = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const DimParams<T>& D = P.dim[d];
+        const int i0 = stencil_w_dw<T, W>(D, __ldcs(D.t_eval + k), w[d], dw[d]);
+        stride[d] = (int)D.u_stride * S;
+        base += (int64_t)i0 * D.u_stride;
+    }
+    const int64_t ko = P.perm ? (int64_t)__ldcs(P.perm + k) : k;
+    const int64_t slot = P.out_comp_stride * C;
+    const GVec<T, (N + 1) * C> g = ContractGV<T, N - 1, W, C, WIDE>::run(P.u_aos + base * S, w, dw, stride);
+    T* o = P.out + ko * P.out_point_stride;
+    if (P.staged_records) {   // cell-sorted plan: the record is g in this order (component fastest, then slot)
+        store_record<T, (N + 1) * C>(o, g.g);
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < N + 1; ++j)
+#pragma unroll
+        for (int c = 0; c < C; ++c) __stcs(o + (int64_t)c * P.out_comp_stride + j * slot, g.g[j * C + c]);
+}
+
 template <typename T, int N, int W>
 cudaError_t launch_gradient(const EvalParams<T>& P, cudaStream_t s) {
-    unstructured_gradient_kernel<T, N, W><<<(unsigned)((P.n_points + GBLOCK - 1) / GBLOCK), GBLOCK, 0, s>>>(P);
+    const unsigned nb = (unsigned)((P.n_points + GBLOCK - 1) / GBLOCK);
+    // vector-valued u with a component-fastest copy at hand (the register budget allows (N + 1) * C <= 16 accumulators)
+    if (P.u_aos && P.n_comp >= 2 && P.n_comp <= 4 && (N + 1) * P.n_comp <= 16 && P.u_comp_stride * aos_node_stride(P.n_comp) < (1LL << 31)) {
+        const bool narrow = sizeof(T) == 8 && P.coherent_points;
+        switch (P.n_comp) {
+            case 2: unstructured_gradient_aos_kernel<T, N, W, 2, true><<<nb, GBLOCK, 0, s>>>(P); break;
+            case 3:
+                if constexpr ((N + 1) * 3 <= 16) {
+                    if (narrow) unstructured_gradient_aos_kernel<T, N, W, 3, sizeof(T) != 8><<<nb, GBLOCK, 0, s>>>(P);
+                    else unstructured_gradient_aos_kernel<T, N, W, 3, true><<<nb, GBLOCK, 0, s>>>(P);
+                }
+                break;
+            default:
+                if constexpr ((N + 1) * 4 <= 16) {
+                    if (narrow) unstructured_gradient_aos_kernel<T, N, W, 4, sizeof(T) != 8><<<nb, GBLOCK, 0, s>>>(P);
+                    else unstructured_gradient_aos_kernel<T, N, W, 4, true><<<nb, GBLOCK, 0, s>>>(P);
+                }
+                break;
+        }
+        return cudaGetLastError();
+    }
+    unstructured_gradient_kernel<T, N, W><<<nb, GBLOCK, 0, s>>>(P);
     return cudaGetLastError();
 }
 

@@ -5,8 +5,8 @@
 // so a C-component stencil gather touches C distant sectors per node (config 5: 32 corners x 4
 // components = 128 scattered 4-byte loads, ~6 KB of HBM traffic per iid point with 64-byte
 // fetches).  The handle keeps a repacked copy u_aos[c + C*i] (one extra pass per dind_set_u, SURVEY.md
-// §7.2 "repack allowed"): all components of a node are one 8/16-byte vector load, two nodes
-// adjacent along axis 1 share a 32-byte sector.  Outputs keep the reference's layout (n_points, out...).
+// §7.2 "repack allowed"): all components of a node are ONE 8/16/32-byte vector load (3-component nodes are
+// padded to 4 so that a node never straddles a 32-byte sector).  Outputs keep the reference's layout (n_points, out...).
 #include "dind_kernels.h"
 
 namespace dind {
@@ -15,34 +15,7 @@ namespace {
 
 constexpr int ABLOCK = 256;
 
-template <typename T, int C>
-struct Vec {
-    T v[C];
-};
-
-// all components of one node: one vector load when the vector is 8 or 16 bytes
-template <typename T, int C>
-__device__ __forceinline__ Vec<T, C> load_node(const T* __restrict__ p) {
-    Vec<T, C> r;
-    if constexpr (sizeof(T) * C == 16) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(p));
-        memcpy(&r, &q, 16);
-    } else if constexpr (sizeof(T) * C == 8) {
-        const float2 q = __ldg(reinterpret_cast<const float2*>(p));
-        memcpy(&r, &q, 8);
-    } else if constexpr (sizeof(T) * C == 32) {
-        const float4 q0 = __ldg(reinterpret_cast<const float4*>(p));
-        const float4 q1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
-        memcpy(&r.v[0], &q0, 16);
-        memcpy(&r.v[C / 2], &q1, 16);
-    } else {
-#pragma unroll
-        for (int c = 0; c < C; ++c) r.v[c] = __ldg(p + c);
-    }
-    return r;
-}
-
-template <typename T, int D, int W, int C>
+template <typename T, int D, int W, int C, bool WIDE>
 struct ContractV {
     static __device__ __forceinline__ Vec<T, C> run(const T* __restrict__ p, const T (&w)[MAXN][W], const int (&stride)[MAXN]) {
         Vec<T, C> acc;
@@ -50,22 +23,22 @@ struct ContractV {
         for (int c = 0; c < C; ++c) acc.v[c] = T(0);
 #pragma unroll
         for (int a = 0; a < W; ++a) {
-            const Vec<T, C> t = ContractV<T, D - 1, W, C>::run(p + a * stride[D], w, stride);
+            const Vec<T, C> t = ContractV<T, D - 1, W, C, WIDE>::run(p + a * stride[D], w, stride);
 #pragma unroll
             for (int c = 0; c < C; ++c) acc.v[c] = fma(w[D][a], t.v[c], acc.v[c]);
         }
         return acc;
     }
 };
-template <typename T, int W, int C>
-struct ContractV<T, 0, W, C> {
+template <typename T, int W, int C, bool WIDE>
+struct ContractV<T, 0, W, C, WIDE> {
     static __device__ __forceinline__ Vec<T, C> run(const T* __restrict__ p, const T (&w)[MAXN][W], const int (&)[MAXN]) {
         Vec<T, C> acc;
 #pragma unroll
         for (int c = 0; c < C; ++c) acc.v[c] = T(0);
 #pragma unroll
         for (int a = 0; a < W; ++a) {
-            const Vec<T, C> t = load_node<T, C>(p + a * C);
+            const Vec<T, C> t = load_node<T, C, WIDE>(p + a * (C == 3 ? 4 : C));
 #pragma unroll
             for (int c = 0; c < C; ++c) acc.v[c] = fma(w[0][a], t.v[c], acc.v[c]);
         }
@@ -92,10 +65,11 @@ __device__ __forceinline__ int stencil_ct(const DimParams<T>& D, T x, int cached
     return idx - W;
 }
 
-template <typename T, int N, int W, int C>
+template <typename T, int N, int W, int C, bool WIDE>
 __global__ void __launch_bounds__(ABLOCK) unstructured_aos_kernel(const __grid_constant__ EvalParams<T> P) {
     const int64_t k = (int64_t)blockIdx.x * ABLOCK + threadIdx.x;
     if (k >= P.n_points) return;
+    constexpr int S = C == 3 ? 4 : C;   // aos_node_stride(C)
     T w[MAXN][W];
     int stride[MAXN];
     int64_t base = 0;
@@ -105,11 +79,11 @@ __global__ void __launch_bounds__(ABLOCK) unstructured_aos_kernel(const __grid_c
         const T x = __ldcs(D.t_eval + k);
         const int cached = P.use_cached_idx ? __ldcs(D.idx_eval + k) : 0;
         const int i0 = stencil_ct<T, W>(D, x, cached, w[d]);
-        stride[d] = (int)D.u_stride * C;
+        stride[d] = (int)D.u_stride * S;
         base += (int64_t)i0 * D.u_stride;
     }
     const int64_t ko = P.perm ? (int64_t)__ldcs(P.perm + k) : k;
-    const Vec<T, C> acc = ContractV<T, N - 1, W, C>::run(P.u_aos + base * C, w, stride);
+    const Vec<T, C> acc = ContractV<T, N - 1, W, C, WIDE>::run(P.u_aos + base * S, w, stride);
     if (P.staged_records) {   // cell-sorted plan: one aligned record per point
         store_record<T, C>(P.out + ko * P.out_point_stride, acc.v);
         return;
@@ -122,16 +96,24 @@ template <typename T>
 __global__ void __launch_bounds__(ABLOCK) aos_repack_kernel(const T* __restrict__ u, T* __restrict__ u_aos, int64_t n, int C) {
     const int64_t i = (int64_t)blockIdx.x * ABLOCK + threadIdx.x;
     if (i >= n) return;
-    for (int c = 0; c < C; ++c) u_aos[i * C + c] = __ldcs(u + i + (int64_t)c * n);
+    const int S = aos_node_stride(C);
+    for (int c = 0; c < S; ++c) u_aos[i * S + c] = c < C ? __ldcs(u + i + (int64_t)c * n) : T(0);
 }
 
 template <typename T, int N, int W>
 cudaError_t launch_aos(const EvalParams<T>& P, cudaStream_t s) {
     const unsigned nb = (unsigned)((P.n_points + ABLOCK - 1) / ABLOCK);
+    const bool narrow = sizeof(T) == 8 && P.coherent_points;   // only 32-byte nodes have two load shapes
     switch (P.n_comp) {
-        case 2: unstructured_aos_kernel<T, N, W, 2><<<nb, ABLOCK, 0, s>>>(P); break;
-        case 3: unstructured_aos_kernel<T, N, W, 3><<<nb, ABLOCK, 0, s>>>(P); break;
-        case 4: unstructured_aos_kernel<T, N, W, 4><<<nb, ABLOCK, 0, s>>>(P); break;
+        case 2: unstructured_aos_kernel<T, N, W, 2, true><<<nb, ABLOCK, 0, s>>>(P); break;
+        case 3:
+            if (narrow) unstructured_aos_kernel<T, N, W, 3, sizeof(T) != 8><<<nb, ABLOCK, 0, s>>>(P);
+            else unstructured_aos_kernel<T, N, W, 3, true><<<nb, ABLOCK, 0, s>>>(P);
+            break;
+        case 4:
+            if (narrow) unstructured_aos_kernel<T, N, W, 4, sizeof(T) != 8><<<nb, ABLOCK, 0, s>>>(P);
+            else unstructured_aos_kernel<T, N, W, 4, true><<<nb, ABLOCK, 0, s>>>(P);
+            break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -154,7 +136,7 @@ bool aos_supported(const EvalParams<T>& P) {
         if (P.dim[d].width != W || P.dim[d].kind == CONSTANT) return false;
         if (P.dim[d].kind == BSPLINE && P.dim[d].degree != W - 1) return false;
     }
-    if (P.u_comp_stride * P.n_comp >= (1LL << 31)) return false;
+    if (P.u_comp_stride * aos_node_stride(P.n_comp) >= (1LL << 31)) return false;
     if (W == 2) return true;
     return (W == 3 || W == 4) && (N == 2 || N == 3);
 }

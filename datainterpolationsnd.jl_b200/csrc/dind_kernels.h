@@ -28,6 +28,8 @@ cudaError_t plan_sort_points(const EvalParams<T>& P, uint32_t* perm, T* const* t
                              size_t* scratch_bytes, cudaStream_t s);
 
 // Component-fastest repack of u for vector-valued unstructured evaluation (dind_fast_unstructured_aos.cu).
+// elements per node of the component-fastest copy: 3 components are padded to 4 (one aligned vector per node)
+__host__ __device__ inline int aos_node_stride(int n_comp) { return n_comp == 3 ? 4 : n_comp; }
 template <typename T> cudaError_t launch_aos_repack(const T* u, T* u_aos, int64_t n, int n_comp, cudaStream_t s);
 template <typename T> bool aos_supported(const EvalParams<T>& P);
 template <typename T> bool try_eval_fast_unstructured_aos(const EvalParams<T>& P, cudaStream_t s, const char** name,
