@@ -114,6 +114,7 @@ struct dind_interp_s {
     DevBuf w_owned;
     DevBuf uw;          // u pre-multiplied by the weights
     bool uw_valid = false;
+    DevBuf split_scratch;   // stage-1 results of the two-stage 4-D grid evaluation
     DevBuf u_aos;       // component-fastest copy of u (vector-valued unstructured evaluation)
     bool u_aos_valid = false;
     // cell-sorted plan for eval_unstructured (dind_plan.cu)
@@ -334,9 +335,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     else n_points = n_eval[0];
     if (n_points == 0) return DIND_OK;
 
-    int rc = ensure_premultiplied<T>(h);
-    if (rc) return rc;
-
+    int rc = DIND_OK;
     EvalParams<T> P;
     memset(&P, 0, sizeof P);
     bool const_deriv = false, zero_result = false;
@@ -378,8 +377,16 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         // (src/interpolation_methods.jl:49-55): keep the caller's values.
         if (untouched_semantics) CUDA_TRY(cudaMemcpyAsync(d_out, out, out_bytes, cudaMemcpyHostToDevice, h->stream));
     }
-    P.u = h->w_set ? (const T*)h->uw.p : (const T*)h->d_u;
     P.wts = h->w_set ? (const T*)h->d_w : nullptr;
+    P.n_in = N;
+    P.u_comp_stride = h->comp_stride;
+    P.n_comp = (int32_t)h->n_comp;
+    // NURBS numerator u*w: a separate pass per dind_set_u, except where the kernel forms it while staging u
+    const bool split = grid && !(flags & DIND_FLAG_GENERIC) && !const_deriv && !zero_result && grid_split_supported<T>(P) &&
+                       !getenv("DIND_NO_SPLIT");
+    P.u_is_raw = split && h->w_set && !h->uw_valid && grid_split_slice_ok<T>(P);
+    if (!P.u_is_raw && (rc = ensure_premultiplied<T>(h))) return rc;
+    P.u = (h->w_set && !P.u_is_raw) ? (const T*)h->uw.p : (const T*)h->d_u;
     P.out = d_out;
     P.n_points = n_points;
     P.u_comp_stride = h->comp_stride;
@@ -504,6 +511,12 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         }
     }
     if (use_aos && !handled) handled = try_eval_fast_unstructured_aos<T>(P, h->stream, &name, &err, &nlaunch);
+    if (split && !handled) {
+        CUDA_TRY(h->split_scratch.ensure(grid_split_scratch_bytes<T>(P)));
+        err = launch_grid_split<T>(P, h->split_scratch.p, h->stream, &name, &nlaunch);
+        handled = err != cudaErrorNotSupported;
+        if (!handled) err = cudaSuccess;
+    }
     if (fast_ok && !handled) {
         handled = grid ? try_eval_fast_grid<T>(P, h->stream, &name, &err, &nlaunch)
                        : try_eval_fast_unstructured<T>(P, h->stream, &name, &err, &nlaunch);
@@ -656,7 +669,7 @@ int dind_destroy(dind_handle_t h) {
         h->dims[d].release();
         h->pts_stage[d].release();
     }
-    h->u_owned.release(); h->w_owned.release(); h->uw.release(); h->u_aos.release(); h->out_stage[0].release(); h->out_stage[1].release();
+    h->u_owned.release(); h->w_owned.release(); h->uw.release(); h->u_aos.release(); h->split_scratch.release(); h->out_stage[0].release(); h->out_stage[1].release();
     if (h->small_host) cudaFreeHost(h->small_host);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_kernel) cudaEventDestroy(h->ev_kernel);

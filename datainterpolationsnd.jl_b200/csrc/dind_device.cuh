@@ -141,6 +141,9 @@ struct EvalParams {
     int32_t zero_result;   // Linear with order > 1 somewhere: result is identically zero
     int32_t use_cached_idx;
     const uint32_t* perm;  // cell-sorted plan: output position of point k of the (sorted) t_eval arrays; null = identity
+    int32_t n_stencil;       // grid: > 0 = dim[0..n_stencil) are the stencil axes and the rest identity/selector ("point") axes,
+                             // already in kernel order (dind_fast_grid_split.cu); 0 = let the dispatcher classify the axes
+    int32_t u_is_raw;        // NURBS: u has NOT been pre-multiplied by the weights (only the split grid path accepts that)
     int32_t coherent_points; // neighbouring points share their stencil (cell-sorted plan): prefer narrow, broadcast loads
     int32_t staged_records;  // out is the plan's staging buffer: component-fastest records of out_point_stride
                              // elements, padded and aligned as plan_record_stride() says (vector stores allowed)
@@ -344,6 +347,27 @@ __device__ __forceinline__ Vec<T, C> load_node(const T* __restrict__ p) {
         for (int c = 0; c < C; ++c) r.v[c] = (T)q[c];
     }
     return r;
+}
+
+// NURBS quotient num / den (src/interpolation_methods.jl:134-138) for the grid kernels, where it is paid per
+// output point.  The IEEE FP64 division is a ~30-instruction routine (ncu: half of all instructions of the
+// config-4 kernels); for a denominator in the normal range this is the hardware reciprocal seed, two Newton
+// steps and one residual correction — within 1 ulp of the IEEE quotient.  Zero, subnormal, huge, Inf and
+// NaN denominators take the IEEE division, so the special values are the reference's.
+template <typename T>
+__device__ __forceinline__ T nurbs_div(T num, T den) {
+    return num / den;
+}
+template <>
+__device__ __forceinline__ double nurbs_div<double>(double num, double den) {
+    const double a = fabs(den);
+    if (!(a > 1e-290 && a < 1e290)) return num / den;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    r = fma(r, fma(-den, r, 1.0), r);
+    r = fma(r, fma(-den, r, 1.0), r);
+    const double q = num * r;
+    return fma(fma(-den, q, num), r, q);
 }
 
 // First stencil node only (the i0 of dim_stencil, without the weights): key of the cell-sorted plan.

@@ -227,7 +227,7 @@ __device__ __forceinline__ void walk_pencil(const EvalParams<T>& P, const Pencil
                             acc = fma(wl[a], A[a][j][v], acc);
                             if (NURBS) den = fma(wl[a], B[NURBS ? a : 0][j][v], den);
                         }
-                        if (FULL || ok[j][v]) __stcs(op[j] + 32 * v, NURBS ? acc / den : acc);
+                        if (FULL || ok[j][v]) __stcs(op[j] + 32 * v, NURBS ? nurbs_div(acc, den) : acc);
                     }
                     op[j] += R;
                 }
@@ -450,14 +450,19 @@ bool try_grid_range(const EvalParams<T>& P0, cudaStream_t s, const char** name, 
     if (W < 1 || W > 4) return false;   // W = 1: all-Constant dimensions (nearest-node lookup)
     EvalParams<T> P = P0;
     int ns = 0, np = 0;
-    int point[MAXN];
-    for (int d = 0; d < NT; ++d) {
-        if (P0.dim[d].width == W) P.dim[ns++] = P0.dim[d];
-        else if (P0.dim[d].width == 1 && d >= 2 && d < NT - 1) point[np++] = d;
-        else return false;
+    if (P0.n_stencil > 0) {   // axes already classified and ordered by the caller
+        ns = P0.n_stencil;
+        np = NT - ns;
+    } else {
+        int point[MAXN];
+        for (int d = 0; d < NT; ++d) {
+            if (P0.dim[d].width == W) P.dim[ns++] = P0.dim[d];
+            else if (P0.dim[d].width == 1 && d >= 2 && d < NT - 1) point[np++] = d;
+            else return false;
+        }
+        if (P0.dim[0].width != W || P0.dim[NT - 1].width != W || (ns >= 3 && P0.dim[1].width != W)) return false;
+        for (int e = 0; e < np; ++e) P.dim[ns + e] = P0.dim[point[e]];
     }
-    if (P0.dim[0].width != W || P0.dim[NT - 1].width != W || (ns >= 3 && P0.dim[1].width != W)) return false;
-    for (int e = 0; e < np; ++e) P.dim[ns + e] = P0.dim[point[e]];
     const int N = ns;
     if (N < NLO || N > NHI || N < 2 || N > 5) return false;
     int64_t total = 1;

@@ -1,0 +1,458 @@
+// dind_fast_grid_split.cu — eval_grid! for 4-D B-spline / NURBS grids as TWO separable stages.
+//
+// The pencil kernel (dind_fast_grid.cuh) contracts axes 1..N-1 inside every thread for each new
+// plane of the last axis: for BASELINE config 4 (4-D, degree 2, NURBS) that is 27 nodes x 2 arrays
+// per thread and plane, re-gathered through L1 by every (g_2, g_3) item — ncu: L1 load wavefronts
+// 86 %, 0.19 of the HBM roofline.  A tensor-product stencil factorises, so the evaluation is split:
+//
+//   stage 1  T(g_1, g_2, i_3, i_4) = sum_{a1,a2} w_1 w_2 u(i_1+a1, i_2+a2, i_3, i_4)
+//            = the 2-D pencil kernel over axes (1, 2) with axes 3 and 4 as identity "point" axes
+//            (NURBS: once for u*w, once for w);
+//   stage 2  out(b, g_3, g_4) = sum_{a3,a4} w_3 w_4 T(b, i_3+a3, i_4+a4),  b = (g_1, g_2) contiguous
+//            = grid_batch_kernel below: lanes along the batch index (every load and store fully
+//            coalesced, all stencil indices and weights warp-uniform), two rows of g_3 per thread,
+//            a sliding window of W planes along axis 4; NURBS divides at the end.
+//
+// FMAs per output drop from ~30 to ~6 (x2 for NURBS) and nothing is gathered; the price is one
+// round trip of T through HBM/L2 (config 4: 2 x 537 MB written and read once).
+#include <algorithm>
+
+#include "dind_kernels.h"
+
+namespace dind {
+
+namespace {
+
+constexpr int SB_BLOCK = 128;
+constexpr int SB_WARPS = SB_BLOCK / 32;
+constexpr int SB_MAXCHUNK = 64;
+constexpr int SB_VB = 2;
+#ifndef SB_PF
+#define SB_PF 1
+#endif
+
+template <typename T>
+struct BatchParams {
+    const T* tn;          // numerator (or the only) stage-1 result, (B, n3, n4)
+    const T* td;          // denominator (NURBS) or null
+    T* out;               // (B, g3, g4)
+    int64_t B;
+    int n3, n4, g3, g4;
+    const int32_t* i0_3;
+    const T* w_3;
+    const int32_t* i0_4;
+    const T* w_4;
+    int chunk;
+    int n_bseg, n_items;
+};
+
+__global__ void iota_kernel(int32_t* p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+// REL = 0 / 1: the two g_3 rows of the thread start at the same node / one node apart and share
+// their W + REL rows of T; REL = 2: unrelated rows (down-sampling, unsorted t_eval), loaded separately.
+template <typename T, int W, bool NURBS, int REL>
+__device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s_i0, const T* s_w, int g_lo, int g_n,
+                                           const int64_t (&boff)[SB_VB], const bool (&okb)[SB_VB], int g3a, bool ok1,
+                                           int i3a, int i3b, const T (&w3)[2][W]) {
+    constexpr int VB = SB_VB;
+    constexpr int ROWS = REL == 2 ? 2 * W : W + REL;
+    T wn[W][2][VB];
+    T wd[NURBS ? W : 1][2][VB];
+#pragma unroll
+    for (int a = 0; a < W; ++a)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int v = 0; v < VB; ++v) {
+                wn[a][j][v] = T(0);
+                if (NURBS) wd[a][j][v] = T(0);
+            }
+    const int64_t Bn3 = Q.B * Q.n3;
+    const T* bn[VB];
+#pragma unroll
+    for (int v = 0; v < VB; ++v) bn[v] = Q.tn + boff[v] + Q.B * (int64_t)i3a;
+    const int64_t dd = NURBS ? Q.td - Q.tn : 0;                       // same offsets in both stage-1 arrays
+    const int64_t rel_b = Q.B * (int64_t)(i3b - i3a - (W - 1));       // REL == 2: jump from row i3a + W - 1 to row i3b
+    int cur = -(1 << 30);
+    const int64_t o_plane = Q.B * Q.g3;
+    T* op[2][VB];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int v = 0; v < VB; ++v) op[j][v] = Q.out + Q.B * ((int64_t)(g3a + j) + (int64_t)Q.g3 * g_lo) + boff[v];
+    for (int g = 0; g < g_n; ++g) {
+        const int i4 = s_i0[g];
+        if (i4 != cur) {   // warp-uniform
+            const int shift = (i4 > cur && i4 - cur < W) ? i4 - cur : W;
+            for (int s = 0; s < shift; ++s) {
+#pragma unroll
+                for (int a = 0; a + 1 < W; ++a)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int v = 0; v < VB; ++v) {
+                            wn[a][j][v] = wn[a + 1][j][v];
+                            if (NURBS) wd[a][j][v] = wd[a + 1][j][v];
+                        }
+                const int pidx = i4 + (W - shift) + s;
+                const bool pf_ok = pidx + SB_PF < Q.n4;
+                const int64_t pl = Bn3 * (int64_t)pidx;
+                T rn[VB][ROWS], rd[VB][NURBS ? ROWS : 1];
+#pragma unroll
+                for (int v = 0; v < VB; ++v) {
+                    const T* q = bn[v] + pl;
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r) {
+                        rn[v][r] = __ldg(q);
+                        if (NURBS) rd[v][r] = __ldg(q + dd);
+                        // the walk is sequential along axis 4: ask for the same rows of the next plane now
+                        if (pf_ok) {
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(q + SB_PF * Bn3));
+                            if (NURBS) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + dd + SB_PF * Bn3));
+                        }
+                        q += (REL == 2 && r == W - 1) ? rel_b : Q.B;
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < VB; ++v)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int r0 = j == 0 ? 0 : (REL == 2 ? W : REL);
+                        T an = T(0), ad = T(0);
+#pragma unroll
+                        for (int a = 0; a < W; ++a) {
+                            an = fma(w3[j][a], rn[v][r0 + a], an);
+                            if (NURBS) ad = fma(w3[j][a], rd[v][r0 + a], ad);
+                        }
+                        wn[W - 1][j][v] = an;
+                        if (NURBS) wd[W - 1][j][v] = ad;
+                    }
+            }
+            cur = i4;
+        }
+        T w4[W];
+#pragma unroll
+        for (int a = 0; a < W; ++a) w4[a] = s_w[g * W + a];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int v = 0; v < VB; ++v) {
+                T an = T(0), ad = T(0);
+#pragma unroll
+                for (int a = 0; a < W; ++a) {
+                    an = fma(w4[a], wn[a][j][v], an);
+                    if (NURBS) ad = fma(w4[a], wd[a][j][v], ad);
+                }
+                if (okb[v] && (j == 0 || ok1)) __stcs(op[j][v], NURBS ? nurbs_div(an, ad) : an);
+                op[j][v] += o_plane;
+            }
+    }
+}
+
+template <typename T, int W, bool NURBS>
+__global__ void __launch_bounds__(SB_BLOCK, 4) grid_batch_kernel(const __grid_constant__ BatchParams<T> Q) {
+    __shared__ int s_i0[SB_MAXCHUNK];
+    __shared__ T s_w[SB_MAXCHUNK * W];
+    const int g_lo = blockIdx.y * Q.chunk;
+    const int g_n = min(Q.g4 - g_lo, Q.chunk);
+    for (int i = threadIdx.x; i < g_n; i += SB_BLOCK) s_i0[i] = __ldg(Q.i0_4 + g_lo + i);
+    for (int i = threadIdx.x; i < g_n * W; i += SB_BLOCK) s_w[i] = __ldg(Q.w_4 + (int64_t)g_lo * W + i);
+    __syncthreads();
+    const int item = blockIdx.x * SB_WARPS + (threadIdx.x >> 5);
+    if (item >= Q.n_items) return;
+    const int lane = threadIdx.x & 31;
+    const int g3p = item / Q.n_bseg;
+    const int bseg = item - g3p * Q.n_bseg;
+    int64_t boff[SB_VB];
+    bool okb[SB_VB];
+#pragma unroll
+    for (int v = 0; v < SB_VB; ++v) {
+        const int64_t b = (int64_t)bseg * (32 * SB_VB) + lane + 32 * v;
+        okb[v] = b < Q.B;
+        boff[v] = okb[v] ? b : Q.B - 1;
+    }
+    const int g3a = g3p * 2;
+    const bool ok1 = g3a + 1 < Q.g3;
+    const int g3b = ok1 ? g3a + 1 : g3a;
+    const int i3a = __ldg(Q.i0_3 + g3a), i3b = __ldg(Q.i0_3 + g3b);
+    T w3[2][W];
+#pragma unroll
+    for (int a = 0; a < W; ++a) {
+        w3[0][a] = __ldg(Q.w_3 + g3a * W + a);
+        w3[1][a] = __ldg(Q.w_3 + g3b * W + a);
+    }
+    const int rel = i3b - i3a;
+    if (rel == 0) batch_walk<T, W, NURBS, 0>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
+    else if (rel == 1) batch_walk<T, W, NURBS, 1>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
+    else batch_walk<T, W, NURBS, 2>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
+}
+
+// ---- stage 1 with the (n_1, n_2) slice of u in shared memory ----------------------------------------
+// One CTA per (i_3, i_4): the slice — contiguous in u — is copied to shared memory once (for NURBS the
+// slices of u*w and of w side by side), then every thread owns one g_1 and a chunk of g_2 and walks it
+// with a sliding window of W plane values (3 conflict-free LDS per new node of axis 2).  Reads of u and
+// writes of T are both fully coalesced; nothing is gathered from global memory.
+constexpr int S1_BLOCK = 256;
+constexpr int S1_CHUNK = 32;
+
+template <typename T>
+struct SliceParams {
+    const T* a0;          // u (or u*w), slices of n1*n2 elements, slice s at a0 + s * slice_stride
+    const T* a1;          // second array (NURBS weights) or null
+    const T* premul;      // NURBS weights to multiply a0 by while it is staged (a0 is the raw u), or null
+    T* t0;                // (g1, g2, slices)
+    T* t1;
+    int n1, n2, g1, g2;
+    int64_t slice_stride;
+    const int32_t* i0_1;
+    const T* w_1;
+    const int32_t* i0_2;
+    const T* w_2;
+};
+
+template <typename T, int W, int NARR>
+__global__ void __launch_bounds__(S1_BLOCK) grid_slice_kernel(const __grid_constant__ SliceParams<T> Q) {
+    extern __shared__ __align__(16) unsigned char s1_smem[];
+    T* S = reinterpret_cast<T*>(s1_smem);   // [NARR][n1 * n2]
+    const int nn = Q.n1 * Q.n2;
+    const int64_t sl = blockIdx.x;
+    {
+        const T* src0 = Q.a0 + sl * Q.slice_stride;
+        const T* srcw = (NARR == 2 ? Q.a1 : Q.premul) + sl * Q.slice_stride;
+        if (NARR == 2 || Q.premul) {
+            // NURBS numerator u*w (src/interpolation_methods.jl:124-131) formed here instead of by a separate pass
+            for (int i = threadIdx.x; i < nn; i += S1_BLOCK) {
+                const T wv = __ldg(srcw + i);
+                S[i] = Q.premul ? __ldcs(src0 + i) * wv : __ldcs(src0 + i);
+                if (NARR == 2) S[nn + i] = wv;
+            }
+        } else {
+            for (int i = threadIdx.x; i < nn; i += S1_BLOCK) S[i] = __ldcs(src0 + i);
+        }
+    }
+    __syncthreads();
+    const int n_chunks = (Q.g2 + S1_CHUNK - 1) / S1_CHUNK;
+    const int n_tasks = Q.g1 * n_chunks;
+    const int64_t out_slice = (int64_t)Q.g1 * Q.g2;
+    for (int task = threadIdx.x; task < n_tasks; task += S1_BLOCK) {
+        const int ch = task / Q.g1;
+        const int g1 = task - ch * Q.g1;
+        const int i1 = __ldg(Q.i0_1 + g1);
+        T w1[W];
+#pragma unroll
+        for (int a = 0; a < W; ++a) w1[a] = __ldg(Q.w_1 + g1 * W + a);
+        T win[NARR][W];
+#pragma unroll
+        for (int k = 0; k < NARR; ++k)
+#pragma unroll
+            for (int a = 0; a < W; ++a) win[k][a] = T(0);
+        int cur = -(1 << 30);
+        const int g_lo = ch * S1_CHUNK, g_hi = min(Q.g2, g_lo + S1_CHUNK);
+        T* o0 = Q.t0 + sl * out_slice + g1;
+        T* o1 = NARR == 2 ? Q.t1 + sl * out_slice + g1 : nullptr;
+        for (int g = g_lo; g < g_hi; ++g) {
+            const int i2 = __ldg(Q.i0_2 + g);
+            if (i2 != cur) {
+                const int shift = (i2 > cur && i2 - cur < W) ? i2 - cur : W;
+                for (int s = 0; s < shift; ++s) {
+                    const T* row = S + i1 + Q.n1 * (i2 + (W - shift) + s);
+#pragma unroll
+                    for (int k = 0; k < NARR; ++k) {
+#pragma unroll
+                        for (int a = 0; a + 1 < W; ++a) win[k][a] = win[k][a + 1];
+                        T acc = T(0);
+#pragma unroll
+                        for (int a = 0; a < W; ++a) acc = fma(w1[a], row[k * nn + a], acc);
+                        win[k][W - 1] = acc;
+                    }
+                }
+                cur = i2;
+            }
+#pragma unroll
+            for (int k = 0; k < NARR; ++k) {
+                T acc = T(0);
+#pragma unroll
+                for (int a = 0; a < W; ++a) acc = fma(__ldg(Q.w_2 + g * W + a), win[k][a], acc);
+                (k == 0 ? o0 : o1)[(int64_t)g * Q.g1] = acc;
+            }
+        }
+    }
+}
+
+template <typename T, int W>
+cudaError_t launch_slice(const SliceParams<T>& Q, int64_t n_slices, cudaStream_t s) {
+    const int narr = Q.a1 ? 2 : 1;
+    const size_t smem = (size_t)narr * Q.n1 * Q.n2 * sizeof(T);
+    cudaError_t e;
+    if (narr == 2) {
+        if ((e = cudaFuncSetAttribute(grid_slice_kernel<T, W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        grid_slice_kernel<T, W, 2><<<(unsigned)n_slices, S1_BLOCK, smem, s>>>(Q);
+    } else {
+        if ((e = cudaFuncSetAttribute(grid_slice_kernel<T, W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        grid_slice_kernel<T, W, 1><<<(unsigned)n_slices, S1_BLOCK, smem, s>>>(Q);
+    }
+    return cudaGetLastError();
+}
+
+template <typename T, int W>
+cudaError_t launch_batch(const BatchParams<T>& Q0, cudaStream_t s) {
+    BatchParams<T> Q = Q0;
+    Q.n_bseg = (int)((Q.B + 32 * SB_VB - 1) / (32 * SB_VB));
+    const int64_t items = (int64_t)Q.n_bseg * ((Q.g3 + 1) / 2);
+    Q.n_items = (int)items;
+    const int bx = (int)((items + SB_WARPS - 1) / SB_WARPS);
+    int chunk = 32;
+    while (chunk > 8 && (int64_t)bx * ((Q.g4 + chunk - 1) / chunk) < 148 * 4 * 2) chunk >>= 1;
+    Q.chunk = chunk;
+    dim3 grid((unsigned)bx, (unsigned)((Q.g4 + chunk - 1) / chunk));
+    if (Q.td) grid_batch_kernel<T, W, true><<<grid, SB_BLOCK, 0, s>>>(Q);
+    else grid_batch_kernel<T, W, false><<<grid, SB_BLOCK, 0, s>>>(Q);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+template <typename T>
+bool grid_split_supported(const EvalParams<T>& P) {
+    if (P.n_in != 4) return false;
+    const int W = P.dim[0].width;
+    if (W != 3 && W != 4) return false;
+    int64_t B = 1, items2 = 1;
+    for (int d = 0; d < 4; ++d) {
+        if (P.dim[d].width != W || P.dim[d].n_eval < 1 || P.dim[d].n_eval >= 65535 || P.dim[d].n_u >= (1 << 20)) return false;
+    }
+    B = P.dim[0].n_eval * P.dim[1].n_eval;
+    items2 = ((B + 63) / 64) * ((P.dim[2].n_eval + 1) / 2);
+    if (B >= (1LL << 31) || items2 >= (1LL << 31) || P.u_comp_stride >= (1LL << 31)) return false;
+    // worth it when the outputs outnumber the nodes along the first two axes (T is not larger than out)
+    return P.dim[2].n_eval * P.dim[3].n_eval >= (int64_t)P.dim[2].n_u * P.dim[3].n_u;
+}
+
+// stage 1 can run from shared memory: the (n_1, n_2) slices (x2 for NURBS) fit and are contiguous in u
+template <typename T>
+bool grid_split_slice_ok(const EvalParams<T>& P) {
+    const int64_t n1 = P.dim[0].n_u, n2 = P.dim[1].n_u, n3 = P.dim[2].n_u;
+    const size_t slice_bytes = (size_t)n1 * n2 * sizeof(T) * (P.wts ? 2 : 1);
+    return slice_bytes <= 96 * 1024 && P.dim[0].u_stride == 1 && P.dim[1].u_stride == n1 && P.dim[2].u_stride == n1 * n2 &&
+           P.dim[3].u_stride == n1 * n2 * n3 && P.dim[0].n_eval < (1 << 24) && !getenv("DIND_NO_SLICE");
+}
+
+template <typename T>
+size_t grid_split_scratch_bytes(const EvalParams<T>& P) {
+    const size_t t_elems = (size_t)P.dim[0].n_eval * P.dim[1].n_eval * P.dim[2].n_u * P.dim[3].n_u;
+    const size_t t_bytes = (t_elems * sizeof(T) + 255) & ~size_t(255);
+    const size_t iota = ((size_t)std::max(P.dim[2].n_u, P.dim[3].n_u) * sizeof(int32_t) + 255) & ~size_t(255);
+    return iota + t_bytes * (P.wts ? 2 : 1);
+}
+
+template <typename T>
+cudaError_t launch_grid_split(const EvalParams<T>& P, void* scratch, cudaStream_t s, const char** name, int* launches) {
+    const int W = P.dim[0].width;
+    const int n3 = P.dim[2].n_u, n4 = P.dim[3].n_u;
+    const int64_t g1 = P.dim[0].n_eval, g2 = P.dim[1].n_eval;
+    const int64_t B = g1 * g2;
+    const size_t t_elems = (size_t)B * n3 * n4;
+    const size_t t_bytes = (t_elems * sizeof(T) + 255) & ~size_t(255);
+    const int n_iota = std::max(n3, n4);
+    const size_t iota_bytes = ((size_t)n_iota * sizeof(int32_t) + 255) & ~size_t(255);
+    int32_t* iota = (int32_t*)scratch;
+    T* tn = (T*)((char*)scratch + iota_bytes);
+    T* td = P.wts ? (T*)((char*)scratch + iota_bytes + t_bytes) : nullptr;
+    iota_kernel<<<(n_iota + 255) / 256, 256, 0, s>>>(iota, n_iota);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    *launches = 1;
+
+    // stage 1.  Preferred: the shared-memory slice kernel (u*w and w in one pass); it needs the (n_1, n_2)
+    // slice(s) to fit in shared memory and to be contiguous in u.  Otherwise: the 2-D pencil kernel over axes
+    // (1, 2) with axes 3, 4 as identity "point" axes that select slices of u one to one.
+    const int n1 = P.dim[0].n_u, n2 = P.dim[1].n_u;
+    const bool use_slice = grid_split_slice_ok<T>(P);
+    if (P.u_is_raw && !use_slice) return cudaErrorInvalidValue;
+    EvalParams<T> P1 = P;
+    P1.n_in = 4;
+    P1.n_stencil = 2;
+    P1.dim[0].out_stride = 1;
+    P1.dim[1].out_stride = g1;
+    for (int d = 2; d < 4; ++d) {
+        P1.dim[d].width = 1;
+        P1.dim[d].n_eval = d == 2 ? n3 : n4;
+        P1.dim[d].tab_i0 = iota;
+        P1.dim[d].tab_w = nullptr;
+    }
+    P1.dim[2].out_stride = B;
+    P1.dim[3].out_stride = B * n3;
+    P1.wts = nullptr;
+    P1.n_comp = 1;
+    P1.n_points = (int64_t)t_elems;
+    P1.out_comp_stride = (int64_t)t_elems;
+    const char* nm = nullptr;
+    int nl = 0;
+    SliceParams<T> S1;
+    S1.n1 = n1; S1.n2 = n2; S1.g1 = (int)g1; S1.g2 = (int)g2;
+    S1.slice_stride = (int64_t)n1 * n2;
+    S1.i0_1 = P.dim[0].tab_i0; S1.w_1 = P.dim[0].tab_w;
+    S1.i0_2 = P.dim[1].tab_i0; S1.w_2 = P.dim[1].tab_w;
+    bool den_done = false;
+    if (td && !use_slice) {
+        P1.u = P.wts;
+        P1.out = td;
+        if (!try_eval_fast_grid<T>(P1, s, &nm, &e, &nl)) return cudaErrorNotSupported;
+        if (e != cudaSuccess) return e;
+        *launches += nl;
+        den_done = true;
+    }
+    for (int c = 0; c < P.n_comp; ++c) {
+        if (use_slice) {
+            S1.a0 = P.u + (int64_t)c * P.u_comp_stride;
+            S1.t0 = tn;
+            S1.a1 = (td && !den_done) ? P.wts : nullptr;   // the denominator rides along with the first component
+            S1.premul = P.u_is_raw ? P.wts : nullptr;
+            S1.t1 = td;
+            e = W == 3 ? launch_slice<T, 3>(S1, (int64_t)n3 * n4, s) : launch_slice<T, 4>(S1, (int64_t)n3 * n4, s);
+            if (e != cudaSuccess) return e;
+            den_done = true;
+            *launches += 1;
+        } else {
+            P1.u = P.u + (int64_t)c * P.u_comp_stride;
+            P1.out = tn;
+            if (!try_eval_fast_grid<T>(P1, s, &nm, &e, &nl)) return cudaErrorNotSupported;
+            if (e != cudaSuccess) return e;
+            *launches += nl;
+        }
+        // stage 2
+        BatchParams<T> Q;
+        Q.tn = tn;
+        Q.td = td;
+        Q.out = P.out + (int64_t)c * P.out_comp_stride;
+        Q.B = B;
+        Q.n3 = n3;
+        Q.n4 = n4;
+        Q.g3 = (int)P.dim[2].n_eval;
+        Q.g4 = (int)P.dim[3].n_eval;
+        Q.i0_3 = P.dim[2].tab_i0;
+        Q.w_3 = P.dim[2].tab_w;
+        Q.i0_4 = P.dim[3].tab_i0;
+        Q.w_4 = P.dim[3].tab_w;
+        Q.chunk = 0;
+        Q.n_bseg = Q.n_items = 0;
+        e = W == 3 ? launch_batch<T, 3>(Q, s) : launch_batch<T, 4>(Q, s);
+        if (e != cudaSuccess) return e;
+        *launches += 1;
+    }
+    *name = W == 3 ? "grid_split<N=2+2,W=3>" : "grid_split<N=2+2,W=4>";
+    return cudaSuccess;
+}
+
+#define DIND_INST(T)                                                                                       \
+    template bool grid_split_supported<T>(const EvalParams<T>&);                                           \
+    template bool grid_split_slice_ok<T>(const EvalParams<T>&);                                            \
+    template size_t grid_split_scratch_bytes<T>(const EvalParams<T>&);                                     \
+    template cudaError_t launch_grid_split<T>(const EvalParams<T>&, void*, cudaStream_t, const char**, int*);
+DIND_INST(float)
+DIND_INST(double)
+
+}  // namespace dind

@@ -39,6 +39,12 @@ template <typename T> bool try_eval_fast_unstructured_aos(const EvalParams<T>& P
 template <typename T> bool try_eval_fast_gradient(const EvalParams<T>& P, cudaStream_t s, const char** name,
                                                   cudaError_t* err, int* launches);
 
+// Two-stage separable evaluation of 4-D B-spline / NURBS grids (dind_fast_grid_split.cu).
+template <typename T> bool grid_split_supported(const EvalParams<T>& P);
+template <typename T> bool grid_split_slice_ok(const EvalParams<T>& P);   // then NURBS may pass the raw u (P.u_is_raw): u*w is formed in the kernel
+template <typename T> size_t grid_split_scratch_bytes(const EvalParams<T>& P);
+template <typename T> cudaError_t launch_grid_split(const EvalParams<T>& P, void* scratch, cudaStream_t s, const char** name, int* launches);
+
 // Two-level un-permutation (dind_plan.cu): slot2[k] = staging slot of plan position k (slots ordered by
 // the window of the destination), dest2[j] = destination of slot j; plan_unbucket copies slot j home.
 cudaError_t plan_bucket_schedule(const uint32_t* perm, uint32_t* slot2, uint32_t* dest2, int64_t n, void* scratch,

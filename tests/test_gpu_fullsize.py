@@ -50,7 +50,7 @@ def test_c2_full_size_properties(D, torch):
     u2 = D.f_empty((n_u,) * 3, np.float32, "cuda"); u2.copy_(torch.rand((n_u,) * 3, generator=gen, device="cuda"))
     itp = D.NDInterpolation(u1, dims)
     o1 = D.eval_grid(itp)
-    assert itp.last_kernel.startswith("grid_pencil")
+    assert itp.last_kernel.startswith(("grid_pencil", "grid_split"))
     assert tuple(o1.shape) == (n_g,) * 3
     # (a) oracle on a random subsample of grid points (as zipped points)
     idx = rng.integers(0, n_g, size=(3, 200_000))
@@ -162,7 +162,7 @@ def test_c4_nurbs_grid_properties(D, torch):
     dims = tuple(D.BSplineInterpolationDimension(t, 2, t_eval=torch.from_numpy(x).cuda()) for t, x in zip(ts, xs))
     itp = D.NDInterpolation(u, dims, cache=D.NURBSWeights(w))
     out = D.eval_grid(itp)
-    assert tuple(out.shape) == (128,) * 4 and itp.last_kernel.startswith("grid_pencil")
+    assert tuple(out.shape) == (128,) * 4 and itp.last_kernel.startswith(("grid_pencil", "grid_split"))
     idx = rng.integers(0, 128, size=(4, 20_000))
     sub = out[tuple(torch.from_numpy(i).cuda() for i in idx)].cpu().numpy()
     ref = O.evaluate(["bspline"] * 4, ts, u.cpu().numpy(), [xs[d][idx[d]] for d in range(4)], degrees=[2] * 4, weights=w.cpu().numpy())

@@ -166,6 +166,33 @@ def test_nurbs_parity(D, dtype, flags, n_in, degree, out_dims):
     H.assert_close(got, ref, dtype, factor=8.0)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("degree,nurbs,out_dims,orders", [
+    (2, True, (), (0, 0, 0, 0)), (2, False, (2,), (0, 1, 0, 1)), (3, True, (2,), (0, 0, 0, 0)), (3, False, (), (1, 0, 2, 0))])
+@pytest.mark.parametrize("layout", ["upsample", "ragged", "unsorted"])
+def test_grid_split_4d_matches_oracle_and_pencil(D, dtype, degree, nurbs, out_dims, orders, layout):
+    """4-D B-spline / NURBS grids go through the two-stage separable path (dind_fast_grid_split.cu) when the
+    grid is at least as fine as the nodes along axes 3 and 4: same numbers as the oracle and as the
+    one-pass kernels (which DIND_FLAG_GENERIC forces)."""
+    rng = np.random.default_rng(900 + degree)
+    kinds, degrees = ("bspline",) * 4, (degree,) * 4
+    ts, u, w = _case(rng, kinds, degrees, (5, 4, 6, 5), out_dims, dtype, nurbs=nurbs)
+    n_g = {"upsample": (70, 9, 14, 12), "ragged": (33, 3, 9, 11), "unsorted": (8, 5, 16, 13)}[layout]
+    xg = []
+    for t, n in zip(ts, n_g):
+        x = rng.uniform(t[0], t[-1], n).astype(dtype)
+        x[0] = t[0]; x[-1] = t[-1]                    # both ends of the knot span are grid points
+        xg.append(x if layout == "unsorted" else np.sort(x))
+    kw = dict(degrees=degrees, weights=w, grid=True, derivative_orders=orders)
+    ref = H.oracle_eval(kinds, ts, u, xg, **kw)
+    got, kernel = H.gpu_eval(D, kinds, ts, u, xg, **kw)
+    assert kernel.startswith("grid_split"), kernel
+    H.assert_close(got, ref, dtype, factor=8.0)
+    gen, kernel_g = H.gpu_eval(D, kinds, ts, u, xg, flags=GENERIC, **kw)
+    assert kernel_g == "generic_grid"
+    H.assert_close(got, gen, dtype, factor=8.0)
+
+
 def test_cached_idx_path_matches(D):
     rng = np.random.default_rng(5)
     kinds, degrees = ("bspline",) * 2, (3, 2)
