@@ -442,6 +442,32 @@ def test_build_caches_is_optional_and_idempotent(D):
         i.close()
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [1, 2047, 2048, 2049, 4097, 70001])
+@pytest.mark.parametrize("comps", [(), (2,), (3,), (4,), (5,)])
+def test_cell_sorted_window_boundaries_and_record_shapes(D, dtype, n, comps):
+    """The plan's two-level un-permutation works in windows of 2048 original points and in staging records of
+    8 / 16 / 32 / n*16 bytes: every window fill level and every record shape must give the unsorted result
+    bit for bit (value and fused gradient), and a re-plan after new t_eval must too."""
+    rng = np.random.default_rng(n + 17 * len(comps) + (comps[0] if comps else 0))
+    ts = [H.knots(rng, 7, dtype), H.knots(rng, 6, dtype)]
+    u = rng.random((7, 6) + comps).astype(dtype)
+    mk = lambda xs: D.NDInterpolation(u, tuple(D.LinearInterpolationDimension(t, t_eval=x) for t, x in zip(ts, xs)))
+    for rep in range(2):
+        xs = [rng.uniform(t[0] - 0.2, t[-1] + 0.2, n).astype(dtype) for t in ts]
+        if rep == 0:
+            a, b = mk(xs), mk(xs)
+        else:
+            a.set_t_eval(xs); b.set_t_eval(xs)          # re-plan on the same handle
+        for orders in [(0, 0), (1, 0)]:
+            np.testing.assert_array_equal(D.eval_unstructured(b, derivative_orders=orders, flags=CELL_SORTED),
+                                          D.eval_unstructured(a, derivative_orders=orders))
+        np.testing.assert_array_equal(D.eval_unstructured_gradient(b, flags=CELL_SORTED), D.eval_unstructured_gradient(a))
+        perm = b.plan_permutation()
+        assert np.array_equal(np.sort(perm), np.arange(n, dtype=np.uint32))
+    a.close(); b.close()
+
+
 def test_empty_and_single_point_batches(D):
     t = np.array([0.0, 1.0, 2.0])
     itp = D.NDInterpolation(np.array([1.0, 2.0, 4.0]), D.LinearInterpolationDimension(t))
