@@ -355,19 +355,28 @@ __device__ __forceinline__ Vec<T, C> load_node(const T* __restrict__ p) {
 // steps and one residual correction — within 1 ulp of the IEEE quotient.  Zero, subnormal, huge, Inf and
 // NaN denominators take the IEEE division, so the special values are the reference's.
 template <typename T>
-__device__ __forceinline__ T nurbs_div(T num, T den) {
+__device__ __forceinline__ bool nurbs_den_is_normal(T den) {
+    const T a = fabs(den);
+    return sizeof(T) == 8 ? (a > T(1e-290) && a < T(1e290)) : (a > T(1e-30) && a < T(1e30));
+}
+// quotient for a denominator that passed nurbs_den_is_normal
+template <typename T>
+__device__ __forceinline__ T nurbs_div_normal(T num, T den) {
     return num / den;
 }
 template <>
-__device__ __forceinline__ double nurbs_div<double>(double num, double den) {
-    const double a = fabs(den);
-    if (!(a > 1e-290 && a < 1e290)) return num / den;
+__device__ __forceinline__ double nurbs_div_normal<double>(double num, double den) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
     r = fma(r, fma(-den, r, 1.0), r);
     r = fma(r, fma(-den, r, 1.0), r);
     const double q = num * r;
     return fma(fma(-den, q, num), r, q);
+}
+template <typename T>
+__device__ __forceinline__ T nurbs_div(T num, T den) {
+    if (sizeof(T) == 8 && nurbs_den_is_normal(den)) return nurbs_div_normal(num, den);
+    return num / den;
 }
 
 // First stencil node only (the i0 of dim_stencil, without the weights): key of the cell-sorted plan.

@@ -51,6 +51,47 @@ __global__ void iota_kernel(int32_t* p, int n) {
     if (i < n) p[i] = i;
 }
 
+// One plane of the window: rows of T for the thread's 2 x VB outputs, contracted along axis 3 into window
+// slot PH.  The slot is a template parameter so that the window never moves between registers: the walk
+// switches (warp-uniformly) on the slot and rotates the three or four axis-4 WEIGHTS instead.
+template <typename T, int W, bool NURBS, int REL, int PH>
+__device__ __forceinline__ void batch_plane(const T* const (&bn)[SB_VB], int64_t pl, int64_t dd, int64_t stepB, int64_t rel_b,
+                                            int64_t pf_off, bool pf_ok, const T (&w3)[2][W], T (&wn)[W][2][SB_VB],
+                                            T (&wd)[NURBS ? W : 1][2][SB_VB]) {
+    constexpr int VB = SB_VB;
+    constexpr int ROWS = REL == 2 ? 2 * W : W + REL;
+    T rn[VB][ROWS], rd[VB][NURBS ? ROWS : 1];
+#pragma unroll
+    for (int v = 0; v < VB; ++v) {
+        const T* q = bn[v] + pl;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            rn[v][r] = __ldg(q);
+            if (NURBS) rd[v][r] = __ldg(q + dd);
+            // the walk is sequential along axis 4: ask for the same rows of the next plane now
+            if (pf_ok) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(q + pf_off));
+                if (NURBS) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + dd + pf_off));
+            }
+            q += (REL == 2 && r == W - 1) ? rel_b : stepB;
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VB; ++v)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int r0 = j == 0 ? 0 : (REL == 2 ? W : REL);
+            T an = T(0), ad = T(0);
+#pragma unroll
+            for (int a = 0; a < W; ++a) {
+                an = fma(w3[j][a], rn[v][r0 + a], an);
+                if (NURBS) ad = fma(w3[j][a], rd[v][r0 + a], ad);
+            }
+            wn[PH][j][v] = an;
+            if (NURBS) wd[PH][j][v] = ad;
+        }
+}
+
 // REL = 0 / 1: the two g_3 rows of the thread start at the same node / one node apart and share
 // their W + REL rows of T; REL = 2: unrelated rows (down-sampling, unsorted t_eval), loaded separately.
 template <typename T, int W, bool NURBS, int REL>
@@ -58,7 +99,6 @@ __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s
                                            const int64_t (&boff)[SB_VB], const bool (&okb)[SB_VB], int g3a, bool ok1,
                                            int i3a, int i3b, const T (&w3)[2][W]) {
     constexpr int VB = SB_VB;
-    constexpr int ROWS = REL == 2 ? 2 * W : W + REL;
     T wn[W][2][VB];
     T wd[NURBS ? W : 1][2][VB];
 #pragma unroll
@@ -77,6 +117,10 @@ __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s
     const int64_t dd = NURBS ? Q.td - Q.tn : 0;                       // same offsets in both stage-1 arrays
     const int64_t rel_b = Q.B * (int64_t)(i3b - i3a - (W - 1));       // REL == 2: jump from row i3a + W - 1 to row i3b
     int cur = -(1 << 30);
+    int phase = 0;            // window slot that receives the next plane; plane cur + a lives in slot (phase + a) % W
+    int rot[W];               // rot[s] = (s - phase) mod W: the axis-4 weight that belongs to slot s
+#pragma unroll
+    for (int sl = 0; sl < W; ++sl) rot[sl] = sl;
     const int64_t o_plane = Q.B * Q.g3;
     T* op[2][VB];
 #pragma unroll
@@ -88,65 +132,58 @@ __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s
         if (i4 != cur) {   // warp-uniform
             const int shift = (i4 > cur && i4 - cur < W) ? i4 - cur : W;
             for (int s = 0; s < shift; ++s) {
-#pragma unroll
-                for (int a = 0; a + 1 < W; ++a)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j)
-#pragma unroll
-                        for (int v = 0; v < VB; ++v) {
-                            wn[a][j][v] = wn[a + 1][j][v];
-                            if (NURBS) wd[a][j][v] = wd[a + 1][j][v];
-                        }
                 const int pidx = i4 + (W - shift) + s;
                 const bool pf_ok = pidx + SB_PF < Q.n4;
                 const int64_t pl = Bn3 * (int64_t)pidx;
-                T rn[VB][ROWS], rd[VB][NURBS ? ROWS : 1];
-#pragma unroll
-                for (int v = 0; v < VB; ++v) {
-                    const T* q = bn[v] + pl;
-#pragma unroll
-                    for (int r = 0; r < ROWS; ++r) {
-                        rn[v][r] = __ldg(q);
-                        if (NURBS) rd[v][r] = __ldg(q + dd);
-                        // the walk is sequential along axis 4: ask for the same rows of the next plane now
-                        if (pf_ok) {
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(q + SB_PF * Bn3));
-                            if (NURBS) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + dd + SB_PF * Bn3));
-                        }
-                        q += (REL == 2 && r == W - 1) ? rel_b : Q.B;
-                    }
+                switch (phase) {
+                    case 0: batch_plane<T, W, NURBS, REL, 0>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd); break;
+                    case 1: batch_plane<T, W, NURBS, REL, 1>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd); break;
+                    case 2: batch_plane<T, W, NURBS, REL, 2>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd); break;
+                    default: batch_plane<T, W, NURBS, REL, W - 1>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd); break;
                 }
-#pragma unroll
-                for (int v = 0; v < VB; ++v)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int r0 = j == 0 ? 0 : (REL == 2 ? W : REL);
-                        T an = T(0), ad = T(0);
-#pragma unroll
-                        for (int a = 0; a < W; ++a) {
-                            an = fma(w3[j][a], rn[v][r0 + a], an);
-                            if (NURBS) ad = fma(w3[j][a], rd[v][r0 + a], ad);
-                        }
-                        wn[W - 1][j][v] = an;
-                        if (NURBS) wd[W - 1][j][v] = ad;
-                    }
+                phase = phase + 1 == W ? 0 : phase + 1;
             }
             cur = i4;
+#pragma unroll
+            for (int sl = 0; sl < W; ++sl) rot[sl] = sl - phase + (sl < phase ? W : 0);
         }
         T w4[W];
 #pragma unroll
-        for (int a = 0; a < W; ++a) w4[a] = s_w[g * W + a];
+        for (int sl = 0; sl < W; ++sl) w4[sl] = s_w[g * W + rot[sl]];
+        T qn[2][VB], qd[2][VB];
+        bool normal = true;
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int v = 0; v < VB; ++v) {
-                T an = T(0), ad = T(0);
+                T an = T(0), ad = T(1);
+                if (NURBS) ad = T(0);
 #pragma unroll
-                for (int a = 0; a < W; ++a) {
-                    an = fma(w4[a], wn[a][j][v], an);
-                    if (NURBS) ad = fma(w4[a], wd[a][j][v], ad);
+                for (int sl = 0; sl < W; ++sl) {
+                    an = fma(w4[sl], wn[sl][j][v], an);
+                    if (NURBS) ad = fma(w4[sl], wd[sl][j][v], ad);
                 }
-                if (okb[v] && (j == 0 || ok1)) __stcs(op[j][v], NURBS ? nurbs_div(an, ad) : an);
+                qn[j][v] = an;
+                qd[j][v] = ad;
+                if (NURBS) normal = normal && nurbs_den_is_normal(ad);
+            }
+        // one (practically never taken) branch per step instead of one per quotient
+        if (NURBS && !normal) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int v = 0; v < VB; ++v) qn[j][v] = qn[j][v] / qd[j][v];
+        } else if (NURBS) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int v = 0; v < VB; ++v) qn[j][v] = nurbs_div_normal(qn[j][v], qd[j][v]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int v = 0; v < VB; ++v) {
+                if (okb[v] && (j == 0 || ok1)) __stcs(op[j][v], qn[j][v]);
                 op[j][v] += o_plane;
             }
     }
