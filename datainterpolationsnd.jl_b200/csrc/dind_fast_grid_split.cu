@@ -54,10 +54,10 @@ __global__ void iota_kernel(int32_t* p, int n) {
 // One plane of the window: rows of T for the thread's 2 x VB outputs, contracted along axis 3 into window
 // slot PH.  The slot is a template parameter so that the window never moves between registers: the walk
 // switches (warp-uniformly) on the slot and rotates the three or four axis-4 WEIGHTS instead.
-template <typename T, int W, bool NURBS, int REL, int PH>
+template <typename T, int W, int W4, bool NURBS, int REL, int PH>
 __device__ __forceinline__ void batch_plane(const T* const (&bn)[SB_VB], int64_t pl, int64_t dd, int64_t stepB, int64_t rel_b,
-                                            int64_t pf_off, bool pf_ok, const T (&w3)[2][W], T (&wn)[W][2][SB_VB],
-                                            T (&wd)[NURBS ? W : 1][2][SB_VB]) {
+                                            int64_t pf_off, bool pf_ok, const T (&w3)[2][W], T (&wn)[W4][2][SB_VB],
+                                            T (&wd)[NURBS ? W4 : 1][2][SB_VB]) {
     constexpr int VB = SB_VB;
     constexpr int ROWS = REL == 2 ? 2 * W : W + REL;
     T rn[VB][ROWS], rd[VB][NURBS ? ROWS : 1];
@@ -94,15 +94,15 @@ __device__ __forceinline__ void batch_plane(const T* const (&bn)[SB_VB], int64_t
 
 // REL = 0 / 1: the two g_3 rows of the thread start at the same node / one node apart and share
 // their W + REL rows of T; REL = 2: unrelated rows (down-sampling, unsorted t_eval), loaded separately.
-template <typename T, int W, bool NURBS, int REL>
+template <typename T, int W, int W4, bool NURBS, int REL>
 __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s_i0, const T* s_w, int g_lo, int g_n,
                                            const int64_t (&boff)[SB_VB], const bool (&okb)[SB_VB], int g3a, bool ok1,
                                            int i3a, int i3b, const T (&w3)[2][W]) {
     constexpr int VB = SB_VB;
-    T wn[W][2][VB];
-    T wd[NURBS ? W : 1][2][VB];
+    T wn[W4][2][VB];
+    T wd[NURBS ? W4 : 1][2][VB];
 #pragma unroll
-    for (int a = 0; a < W; ++a)
+    for (int a = 0; a < W4; ++a)
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -118,9 +118,9 @@ __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s
     const int64_t rel_b = Q.B * (int64_t)(i3b - i3a - (W - 1));       // REL == 2: jump from row i3a + W - 1 to row i3b
     int cur = -(1 << 30);
     int phase = 0;            // window slot that receives the next plane; plane cur + a lives in slot (phase + a) % W
-    int rot[W];               // rot[s] = (s - phase) mod W: the axis-4 weight that belongs to slot s
+    int rot[W4];               // rot[s] = (s - phase) mod W: the axis-4 weight that belongs to slot s
 #pragma unroll
-    for (int sl = 0; sl < W; ++sl) rot[sl] = sl;
+    for (int sl = 0; sl < W4; ++sl) rot[sl] = sl;
     const int64_t o_plane = Q.B * Q.g3;
     T* op[2][VB];
 #pragma unroll
@@ -130,26 +130,30 @@ __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s
     for (int g = 0; g < g_n; ++g) {
         const int i4 = s_i0[g];
         if (i4 != cur) {   // warp-uniform
-            const int shift = (i4 > cur && i4 - cur < W) ? i4 - cur : W;
+            const int shift = (i4 > cur && i4 - cur < W4) ? i4 - cur : W4;
             for (int s = 0; s < shift; ++s) {
-                const int pidx = i4 + (W - shift) + s;
+                const int pidx = i4 + (W4 - shift) + s;
                 const bool pf_ok = pidx + SB_PF < Q.n4;
                 const int64_t pl = Bn3 * (int64_t)pidx;
-                switch (phase) {
-                    case 0: batch_plane<T, W, NURBS, REL, 0>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd); break;
-                    case 1: batch_plane<T, W, NURBS, REL, 1>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd); break;
-                    case 2: batch_plane<T, W, NURBS, REL, 2>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd); break;
-                    default: batch_plane<T, W, NURBS, REL, W - 1>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd); break;
+                if (W4 == 1 || phase == 0) batch_plane<T, W, W4, NURBS, REL, 0>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
+                if constexpr (W4 > 1) {
+                    if (phase == 1) batch_plane<T, W, W4, NURBS, REL, 1>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
                 }
-                phase = phase + 1 == W ? 0 : phase + 1;
+                if constexpr (W4 > 2) {
+                    if (phase == 2) batch_plane<T, W, W4, NURBS, REL, 2>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
+                }
+                if constexpr (W4 > 3) {
+                    if (phase == 3) batch_plane<T, W, W4, NURBS, REL, 3>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
+                }
+                phase = phase + 1 == W4 ? 0 : phase + 1;
             }
             cur = i4;
 #pragma unroll
-            for (int sl = 0; sl < W; ++sl) rot[sl] = sl - phase + (sl < phase ? W : 0);
+            for (int sl = 0; sl < W4; ++sl) rot[sl] = sl - phase + (sl < phase ? W4 : 0);
         }
-        T w4[W];
+        T w4[W4];
 #pragma unroll
-        for (int sl = 0; sl < W; ++sl) w4[sl] = s_w[g * W + rot[sl]];
+        for (int sl = 0; sl < W4; ++sl) w4[sl] = s_w[g * W4 + rot[sl]];
         T qn[2][VB], qd[2][VB];
         bool normal = true;
 #pragma unroll
@@ -159,7 +163,7 @@ __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s
                 T an = T(0), ad = T(1);
                 if (NURBS) ad = T(0);
 #pragma unroll
-                for (int sl = 0; sl < W; ++sl) {
+                for (int sl = 0; sl < W4; ++sl) {
                     an = fma(w4[sl], wn[sl][j][v], an);
                     if (NURBS) ad = fma(w4[sl], wd[sl][j][v], ad);
                 }
@@ -189,14 +193,14 @@ __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s
     }
 }
 
-template <typename T, int W, bool NURBS>
+template <typename T, int W, int W4, bool NURBS>
 __global__ void __launch_bounds__(SB_BLOCK, 4) grid_batch_kernel(const __grid_constant__ BatchParams<T> Q) {
     __shared__ int s_i0[SB_MAXCHUNK];
-    __shared__ T s_w[SB_MAXCHUNK * W];
+    __shared__ T s_w[SB_MAXCHUNK * W4];
     const int g_lo = blockIdx.y * Q.chunk;
     const int g_n = min(Q.g4 - g_lo, Q.chunk);
     for (int i = threadIdx.x; i < g_n; i += SB_BLOCK) s_i0[i] = __ldg(Q.i0_4 + g_lo + i);
-    for (int i = threadIdx.x; i < g_n * W; i += SB_BLOCK) s_w[i] = __ldg(Q.w_4 + (int64_t)g_lo * W + i);
+    for (int i = threadIdx.x; i < g_n * W4; i += SB_BLOCK) s_w[i] = __ldg(Q.w_4 + (int64_t)g_lo * W4 + i);
     __syncthreads();
     const int item = blockIdx.x * SB_WARPS + (threadIdx.x >> 5);
     if (item >= Q.n_items) return;
@@ -222,9 +226,9 @@ __global__ void __launch_bounds__(SB_BLOCK, 4) grid_batch_kernel(const __grid_co
         w3[1][a] = __ldg(Q.w_3 + g3b * W + a);
     }
     const int rel = i3b - i3a;
-    if (rel == 0) batch_walk<T, W, NURBS, 0>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
-    else if (rel == 1) batch_walk<T, W, NURBS, 1>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
-    else batch_walk<T, W, NURBS, 2>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
+    if (rel == 0) batch_walk<T, W, W4, NURBS, 0>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
+    else if (rel == 1) batch_walk<T, W, W4, NURBS, 1>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
+    else batch_walk<T, W, W4, NURBS, 2>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
 }
 
 // ---- stage 1 with the (n_1, n_2) slice of u in shared memory ----------------------------------------
@@ -334,7 +338,7 @@ cudaError_t launch_slice(const SliceParams<T>& Q, int64_t n_slices, cudaStream_t
     return cudaGetLastError();
 }
 
-template <typename T, int W>
+template <typename T, int W, int W4>
 cudaError_t launch_batch(const BatchParams<T>& Q0, cudaStream_t s) {
     BatchParams<T> Q = Q0;
     Q.n_bseg = (int)((Q.B + 32 * SB_VB - 1) / (32 * SB_VB));
@@ -345,8 +349,8 @@ cudaError_t launch_batch(const BatchParams<T>& Q0, cudaStream_t s) {
     while (chunk > 8 && (int64_t)bx * ((Q.g4 + chunk - 1) / chunk) < 148 * 4 * 2) chunk >>= 1;
     Q.chunk = chunk;
     dim3 grid((unsigned)bx, (unsigned)((Q.g4 + chunk - 1) / chunk));
-    if (Q.td) grid_batch_kernel<T, W, true><<<grid, SB_BLOCK, 0, s>>>(Q);
-    else grid_batch_kernel<T, W, false><<<grid, SB_BLOCK, 0, s>>>(Q);
+    if (Q.td) grid_batch_kernel<T, W, W4, true><<<grid, SB_BLOCK, 0, s>>>(Q);
+    else grid_batch_kernel<T, W, W4, false><<<grid, SB_BLOCK, 0, s>>>(Q);
     return cudaGetLastError();
 }
 
@@ -359,7 +363,9 @@ bool grid_split_supported(const EvalParams<T>& P) {
     if (W != 3 && W != 4) return false;
     int64_t B = 1, items2 = 1;
     for (int d = 0; d < 4; ++d) {
-        if (P.dim[d].width != W || P.dim[d].n_eval < 1 || P.dim[d].n_eval >= 65535 || P.dim[d].n_u >= (1 << 20)) return false;
+        if (P.dim[d].n_eval < 1 || P.dim[d].n_eval >= 65535 || P.dim[d].n_u >= (1 << 20)) return false;
+        // axes 1, 2: B-spline of one width; axes 3, 4: that width, or a Constant axis (width 1: a slice selector)
+        if (P.dim[d].width != W && !(d >= 2 && P.dim[d].width == 1)) return false;
     }
     B = P.dim[0].n_eval * P.dim[1].n_eval;
     items2 = ((B + 63) / 64) * ((P.dim[2].n_eval + 1) / 2);
@@ -476,11 +482,17 @@ cudaError_t launch_grid_split(const EvalParams<T>& P, void* scratch, cudaStream_
         Q.w_4 = P.dim[3].tab_w;
         Q.chunk = 0;
         Q.n_bseg = Q.n_items = 0;
-        e = W == 3 ? launch_batch<T, 3>(Q, s) : launch_batch<T, 4>(Q, s);
+        const int W3 = P.dim[2].width, W4 = P.dim[3].width;
+#define DIND_BATCH(A, B4) \
+    if (W3 == A && W4 == B4) e = launch_batch<T, A, B4>(Q, s); else
+        DIND_BATCH(3, 3) DIND_BATCH(4, 4) DIND_BATCH(1, 3) DIND_BATCH(3, 1) DIND_BATCH(1, 4) DIND_BATCH(4, 1) DIND_BATCH(1, 1)
+        e = cudaErrorNotSupported;
+#undef DIND_BATCH
         if (e != cudaSuccess) return e;
         *launches += 1;
     }
-    *name = W == 3 ? "grid_split<N=2+2,W=3>" : "grid_split<N=2+2,W=4>";
+    *name = (P.dim[2].width == W && P.dim[3].width == W) ? (W == 3 ? "grid_split<N=2+2,W=3>" : "grid_split<N=2+2,W=4>")
+                                                         : (W == 3 ? "grid_split<N=2+2,W=3,selector axes>" : "grid_split<N=2+2,W=4,selector axes>");
     return cudaSuccess;
 }
 

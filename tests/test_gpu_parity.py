@@ -193,6 +193,43 @@ def test_grid_split_4d_matches_oracle_and_pencil(D, dtype, degree, nurbs, out_di
     H.assert_close(got, gen, dtype, factor=8.0)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("const_axis", [2, 3])
+@pytest.mark.parametrize("degree,nurbs,out_dims", [(2, True, ()), (3, False, (2,)), (2, False, ())])
+def test_grid_split_4d_with_constant_selector_axis(D, dtype, const_axis, degree, nurbs, out_dims):
+    """BASELINE config 4's mixed variant (a Constant dimension next to B-spline ones) through the two-stage
+    path: the Constant axis only selects a slice in stage 2.  Pinned by the oracle's tensor-product semantics
+    and by slice equivalence with the pure B-spline evaluation on the selected slices."""
+    rng = np.random.default_rng(950 + degree + const_axis)
+    kinds = tuple("constant" if d == const_axis else "bspline" for d in range(4))
+    degrees = tuple(0 if d == const_axis else degree for d in range(4))
+    ts, u, w = _case(rng, kinds, degrees, (5, 4, 6, 5), out_dims, dtype, nurbs=nurbs)
+    xg = []
+    for d, (t, n) in enumerate(zip(ts, (40, 7, 13, 12))):
+        x = np.sort(rng.uniform(t[0], t[-1], n).astype(dtype))
+        if d == const_axis:
+            x[:3] = t[:3]                    # exactly on knots, and beyond the last knot
+            x[-1] = t[-1] + dtype(0.25)
+            x = np.sort(x)
+        xg.append(x)
+    kw = dict(degrees=degrees, weights=w, grid=True)
+    ref = H.oracle_eval(kinds, ts, u, xg, **kw)
+    got, kernel = H.gpu_eval(D, kinds, ts, u, xg, **kw)
+    assert kernel.startswith("grid_split") and "selector" in kernel, kernel
+    H.assert_close(got, ref, dtype, factor=8.0)
+    # slice equivalence: fix the Constant axis at the node the reference's index rule picks
+    tc = ts[const_axis]
+    j = np.clip(np.searchsorted(tc, xg[const_axis], side="right"), 1, tc.size - 1) - 1
+    j = np.where(xg[const_axis] >= tc[-1], tc.size - 1, j)
+    rest = [d for d in range(4) if d != const_axis]
+    for gi in (0, 2, len(j) - 1):
+        us = np.take(u, j[gi], axis=const_axis)
+        ws = None if w is None else np.take(w, j[gi], axis=const_axis)
+        sl = H.oracle_eval(("bspline",) * 3, [ts[d] for d in rest], us, [xg[d] for d in rest],
+                           degrees=(degree,) * 3, weights=ws, grid=True)
+        H.assert_close(np.take(got, gi, axis=const_axis), sl, dtype, factor=8.0)
+
+
 def test_cached_idx_path_matches(D):
     rng = np.random.default_rng(5)
     kinds, degrees = ("bspline",) * 2, (3, 2)
