@@ -146,12 +146,9 @@ cudaError_t plan_unbucket(const T* staged, const uint32_t* dest2, T* out, int64_
     const int cg_max = (96 * 1024) / (UNB_W * (int)sizeof(T));   // components per round: <= 96 KB of shared memory
     const int cg = ct < cg_max ? ct : cg_max;
     const size_t smem = (size_t)cg * UNB_W * sizeof(T);
-    static bool attr_set = false;   // per template instance
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(plan_unbucket_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    // per device (a process may hold handles on several devices), and cheap: set it on every launch
+    cudaError_t e = cudaFuncSetAttribute(plan_unbucket_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return e;
     plan_unbucket_kernel<T><<<(unsigned)((n + UNB_W - 1) / UNB_W), UNB_BLOCK, smem, s>>>(staged, dest2, out, n, ct, rec_stride, cg);
     return cudaGetLastError();
 }
