@@ -382,8 +382,12 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     P.u_comp_stride = h->comp_stride;
     P.n_comp = (int32_t)h->n_comp;
     // NURBS numerator u*w: a separate pass per dind_set_u, except where the kernel forms it while staging u
-    const bool split = grid && !(flags & DIND_FLAG_GENERIC) && !const_deriv && !zero_result && grid_split_supported<T>(P) &&
-                       !getenv("DIND_NO_SPLIT");
+    bool split = grid && !(flags & DIND_FLAG_GENERIC) && !const_deriv && !zero_result && grid_split_supported<T>(P) &&
+                 !getenv("DIND_NO_SPLIT");
+    if (split && h->split_scratch.ensure(grid_split_scratch_bytes<T>(P)) != cudaSuccess) {
+        cudaGetLastError();   // no room for the stage-1 results (at most 2x the size of out): one-pass kernel instead
+        split = false;
+    }
     P.u_is_raw = split && h->w_set && !h->uw_valid && grid_split_slice_ok<T>(P);
     if (!P.u_is_raw && (rc = ensure_premultiplied<T>(h))) return rc;
     P.u = (h->w_set && !P.u_is_raw) ? (const T*)h->uw.p : (const T*)h->d_u;
@@ -512,7 +516,6 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     }
     if (use_aos && !handled) handled = try_eval_fast_unstructured_aos<T>(P, h->stream, &name, &err, &nlaunch);
     if (split && !handled) {
-        CUDA_TRY(h->split_scratch.ensure(grid_split_scratch_bytes<T>(P)));
         err = launch_grid_split<T>(P, h->split_scratch.p, h->stream, &name, &nlaunch);
         handled = err != cudaErrorNotSupported;
         if (!handled) err = cudaSuccess;

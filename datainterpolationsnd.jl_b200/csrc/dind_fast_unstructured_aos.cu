@@ -187,7 +187,7 @@ template <typename T, int N, int W>
 cudaError_t launch_aos(const EvalParams<T>& P, cudaStream_t s) {
     const unsigned nb = (unsigned)((P.n_points + ABLOCK - 1) / ABLOCK);
     const bool narrow = sizeof(T) == 8 && P.coherent_points;   // only 32-byte nodes have two load shapes
-    if (P.coherent_points && !P.use_cached_idx && W >= 3 && !getenv("DIND_NO_PAIR")) {
+    if (P.coherent_points && !P.use_cached_idx && W >= 3 && getenv("DIND_PAIR")) {   // opt-in until measured
         const unsigned nbp = (unsigned)(((P.n_points + 1) / 2 + ABLOCK - 1) / ABLOCK);
         switch (P.n_comp) {
             case 2: unstructured_aos_pair_kernel<T, N, W, 2, true><<<nbp, ABLOCK, 0, s>>>(P); break;
