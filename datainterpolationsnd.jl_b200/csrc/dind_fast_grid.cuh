@@ -43,6 +43,10 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* addr, uint32_t byte
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(addr), "r"(bytes) : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* addr) {   // SASS: CCTL.E.PF1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(addr));
+}
+
 template <int W, int N>
 struct MidCount { static constexpr int value = (N <= 3) ? 1 : (N == 4) ? W : W * W; };
 
@@ -58,6 +62,8 @@ struct PencilCtx {
     int row0;          // offset of output j=0's first row (axis 2)
     int rel_rows;      // first row of output j=1 relative to output j=0's
     int s1, sN;
+    int pf1;           // L1 prefetch distance in nodes along the last axis (0 = off)
+    int pf_off;        // this lane's share of the warp's plane footprint (one 128-byte line per lane), -1 = none
 };
 
 // REL: 0/1 = the J=2 outputs' axis-2 stencils start REL rows apart and share rows; 2 = unrelated rows.
@@ -212,6 +218,12 @@ __device__ __forceinline__ void walk_pencil(const EvalParams<T>& P, const Pencil
             }
             cur = i0;
             if constexpr (PF) plane_load<T, N, W, VX, J, REL>(C, pu, min(cur + W, nN - 1), pend_raw);
+            // one instruction per warp and run: every lane asks L1 for one line of the plane pf1 nodes ahead
+            if (C.pf1 > 0 && C.pf_off >= 0) {
+                const int64_t o = C.pf_off + (int64_t)min(cur + W + C.pf1 - (PF ? 0 : 1), nN - 1) * C.sN;
+                prefetch_l1(uc + o);
+                if (NURBS) prefetch_l1(P.wts + o);
+            }
             // branch-free inner loop over the outputs of this run
             for (; g < g_end; ++g) {
                 T wl[W];
@@ -240,7 +252,7 @@ __device__ __forceinline__ void walk_pencil(const EvalParams<T>& P, const Pencil
 // over `chunk` coordinates of the last axis.
 template <typename T, int N, int W, int VX, int J, bool NURBS, bool FULL, bool PF>
 __global__ void __launch_bounds__(PBLOCK, PF ? 5 : ((sizeof(T) == 8 || W >= 3 || N >= 4) ? 4 : 8)) grid_pencil_kernel(const __grid_constant__ EvalParams<T> P, int n_items, int nseg,
-                                                             int n2g, int chunk, int l2_warm) {
+                                                             int n2g, int chunk, int l2_warm, int pf1) {
     using Ctx = PencilCtx<T, N, W, VX, J>;
     __shared__ int s_i0[MAXCHUNK];
     __shared__ T s_w[MAXCHUNK * W];
@@ -376,6 +388,30 @@ __global__ void __launch_bounds__(PBLOCK, PF ? 5 : ((sizeof(T) == 8 || W >= 3 ||
 #pragma unroll
     for (int v = 0; v < VX; ++v) C.off1[v] += base;
     C.sN = (int)L.u_stride;
+    C.pf1 = pf1;
+    C.pf_off = -1;
+    constexpr int PF_NRMAX = Ctx::MID * ((N < 3) ? 1 : (J == 1 ? W : 2 * W));
+    if (pf1 > 0 && PF_NRMAX <= 32) {
+        // lane -> (middle stencil point, row, 128-byte segment) of the warp's footprint in one plane of u: rows
+        // as plane_load walks them, segments from lane 0's first node of output 0 up to lane 31's last node of
+        // output VX-1
+        constexpr int SEGS = 32 / PF_NRMAX;
+        constexpr int EL = 128 / (int)sizeof(T);
+        const int first = __shfl_sync(0xffffffffu, C.off1[0], 0);
+        const int last = __shfl_sync(0xffffffffu, C.off1[VX - 1], 31) + W - 1;
+        const int mr = lane / SEGS, seg = lane - mr * SEGS;
+        const int m = mr % Ctx::MID, row = mr / Ctx::MID;
+        const bool unrel = !(rel == 0 || rel == 1);
+        const int nrows = (N < 3) ? 1 : (J == 1 ? W : (unrel ? 2 * W : W + rel));
+        if (row < nrows && first + seg * EL <= last) {
+            const int ro = (row < W || !unrel) ? row : rel + row - W;
+            int omm = 0;
+#pragma unroll
+            for (int q2 = 0; q2 < Ctx::MID; ++q2) if (q2 == m) omm = C.om[q2];
+            const int64_t o = (int64_t)first + omm + C.row0 + (int64_t)ro * C.s1 + seg * EL;
+            if (o + (int64_t)(P.dim[N - 1].n_u - 1) * C.sN < P.u_comp_stride) C.pf_off = (int)o;
+        }
+    }
     const int64_t R = L.out_stride;              // points per last-axis coordinate
     out_off += (int64_t)g_lo * R;
     const int64_t jstride = (N >= 3) ? P.dim[1].out_stride : 0;
@@ -408,15 +444,18 @@ cudaError_t launch_pencil_cfg(const EvalParams<T>& P, cudaStream_t s) {
     l2_warm = env_int("DIND_L2_WARM", l2_warm);
     const bool full = n1 % (32 * VX) == 0 && (N < 3 || P.dim[1].n_eval % J == 0);
     const bool pf = env_int("DIND_PF", 1) != 0;
+    // L1 prefetch distance, measured: config 2 0 -> 0.133 ms, 1..3 -> 0.122 ms, 6 -> 0.128 ms; every W = 2 / 3 case
+    // of scripts/sanity_perf.py gains 2-16 %, the W = 4 cases (long runs, 3-4x upsampling) lose 3-6 %
+    const int pf1 = env_int("DIND_PF1", W <= 3 ? 2 : 0);
     if (P.wts) {
-        if (full) grid_pencil_kernel<T, N, W, VX, J, true, true, false><<<grid, PBLOCK, 0, s>>>(P, (int)items, nseg, n2g, chunk, l2_warm);
-        else grid_pencil_kernel<T, N, W, VX, J, true, false, false><<<grid, PBLOCK, 0, s>>>(P, (int)items, nseg, n2g, chunk, l2_warm);
+        if (full) grid_pencil_kernel<T, N, W, VX, J, true, true, false><<<grid, PBLOCK, 0, s>>>(P, (int)items, nseg, n2g, chunk, l2_warm, pf1);
+        else grid_pencil_kernel<T, N, W, VX, J, true, false, false><<<grid, PBLOCK, 0, s>>>(P, (int)items, nseg, n2g, chunk, l2_warm, pf1);
     } else if (sizeof(T) == 4 && W == 2 && pf) {
-        if (full) grid_pencil_kernel<T, N, W, VX, J, false, true, true><<<grid, PBLOCK, 0, s>>>(P, (int)items, nseg, n2g, chunk, l2_warm);
-        else grid_pencil_kernel<T, N, W, VX, J, false, false, true><<<grid, PBLOCK, 0, s>>>(P, (int)items, nseg, n2g, chunk, l2_warm);
+        if (full) grid_pencil_kernel<T, N, W, VX, J, false, true, true><<<grid, PBLOCK, 0, s>>>(P, (int)items, nseg, n2g, chunk, l2_warm, pf1);
+        else grid_pencil_kernel<T, N, W, VX, J, false, false, true><<<grid, PBLOCK, 0, s>>>(P, (int)items, nseg, n2g, chunk, l2_warm, pf1);
     } else {
-        if (full) grid_pencil_kernel<T, N, W, VX, J, false, true, false><<<grid, PBLOCK, 0, s>>>(P, (int)items, nseg, n2g, chunk, l2_warm);
-        else grid_pencil_kernel<T, N, W, VX, J, false, false, false><<<grid, PBLOCK, 0, s>>>(P, (int)items, nseg, n2g, chunk, l2_warm);
+        if (full) grid_pencil_kernel<T, N, W, VX, J, false, true, false><<<grid, PBLOCK, 0, s>>>(P, (int)items, nseg, n2g, chunk, l2_warm, pf1);
+        else grid_pencil_kernel<T, N, W, VX, J, false, false, false><<<grid, PBLOCK, 0, s>>>(P, (int)items, nseg, n2g, chunk, l2_warm, pf1);
     }
     return cudaGetLastError();
 }

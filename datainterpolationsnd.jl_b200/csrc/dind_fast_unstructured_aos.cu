@@ -92,89 +92,6 @@ __global__ void __launch_bounds__(ABLOCK) unstructured_aos_kernel(const __grid_c
     for (int c = 0; c < C; ++c) __stcs(P.out + (int64_t)c * P.out_comp_stride + ko * P.out_point_stride, acc.v[c]);
 }
 
-// ---- two plan-sorted points per thread ---------------------------------------------------------------
-// In plan order consecutive points mostly lie in the same cell (config 3: ~10 points per cell).  The
-// coherent kernel above is bound by the NUMBER of load instructions (ncu: L1 request rate 78 %, 241 loads
-// per point, every one a broadcast hit); a thread that owns two consecutive points of one cell loads each
-// node once and feeds two accumulators.  Points of different cells fall back to two separate contractions.
-template <typename T, int D, int W, int C, bool WIDE>
-struct ContractV2 {
-    static __device__ __forceinline__ void run(const T* __restrict__ p, const T (&w0)[MAXN][W], const T (&w1)[MAXN][W],
-                                               const int (&stride)[MAXN], Vec<T, C>& a0, Vec<T, C>& a1) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) a0.v[c] = a1.v[c] = T(0);
-#pragma unroll
-        for (int a = 0; a < W; ++a) {
-            Vec<T, C> s0, s1;
-            ContractV2<T, D - 1, W, C, WIDE>::run(p + a * stride[D], w0, w1, stride, s0, s1);
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                a0.v[c] = fma(w0[D][a], s0.v[c], a0.v[c]);
-                a1.v[c] = fma(w1[D][a], s1.v[c], a1.v[c]);
-            }
-        }
-    }
-};
-template <typename T, int W, int C, bool WIDE>
-struct ContractV2<T, 0, W, C, WIDE> {
-    static __device__ __forceinline__ void run(const T* __restrict__ p, const T (&w0)[MAXN][W], const T (&w1)[MAXN][W],
-                                               const int (&)[MAXN], Vec<T, C>& a0, Vec<T, C>& a1) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) a0.v[c] = a1.v[c] = T(0);
-#pragma unroll
-        for (int a = 0; a < W; ++a) {
-            const Vec<T, C> t = load_node<T, C, WIDE>(p + a * (C == 3 ? 4 : C));
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                a0.v[c] = fma(w0[0][a], t.v[c], a0.v[c]);
-                a1.v[c] = fma(w1[0][a], t.v[c], a1.v[c]);
-            }
-        }
-    }
-};
-
-template <typename T, int C>
-__device__ __forceinline__ void store_point(const EvalParams<T>& P, int64_t ko, const Vec<T, C>& acc) {
-    if (P.staged_records) {   // cell-sorted plan: one aligned record per point
-        store_record<T, C>(P.out + ko * P.out_point_stride, acc.v);
-        return;
-    }
-#pragma unroll
-    for (int c = 0; c < C; ++c) __stcs(P.out + (int64_t)c * P.out_comp_stride + ko * P.out_point_stride, acc.v[c]);
-}
-
-template <typename T, int N, int W, int C, bool WIDE>
-__global__ void __launch_bounds__(ABLOCK, 2) unstructured_aos_pair_kernel(const __grid_constant__ EvalParams<T> P) {
-    const int64_t k0 = ((int64_t)blockIdx.x * ABLOCK + threadIdx.x) * 2;
-    if (k0 >= P.n_points) return;
-    const bool two = k0 + 1 < P.n_points;
-    const int64_t k1 = two ? k0 + 1 : k0;
-    constexpr int S = C == 3 ? 4 : C;   // aos_node_stride(C)
-    T w0[MAXN][W], w1[MAXN][W];
-    int stride[MAXN];
-    int64_t base0 = 0, base1 = 0;
-#pragma unroll
-    for (int d = 0; d < N; ++d) {
-        const DimParams<T>& D = P.dim[d];
-        const int i0 = stencil_ct<T, W>(D, __ldcs(D.t_eval + k0), 0, w0[d]);
-        const int i1 = stencil_ct<T, W>(D, __ldcs(D.t_eval + k1), 0, w1[d]);
-        stride[d] = (int)D.u_stride * S;
-        base0 += (int64_t)i0 * D.u_stride;
-        base1 += (int64_t)i1 * D.u_stride;
-    }
-    const int64_t ko0 = P.perm ? (int64_t)__ldcs(P.perm + k0) : k0;
-    const int64_t ko1 = P.perm ? (int64_t)__ldcs(P.perm + k1) : k1;
-    Vec<T, C> a0, a1;
-    if (base0 == base1) {
-        ContractV2<T, N - 1, W, C, WIDE>::run(P.u_aos + base0 * S, w0, w1, stride, a0, a1);
-    } else {
-        a0 = ContractV<T, N - 1, W, C, WIDE>::run(P.u_aos + base0 * S, w0, stride);
-        a1 = ContractV<T, N - 1, W, C, WIDE>::run(P.u_aos + base1 * S, w1, stride);
-    }
-    store_point<T, C>(P, ko0, a0);
-    if (two) store_point<T, C>(P, ko1, a1);
-}
-
 template <typename T>
 __global__ void __launch_bounds__(ABLOCK) aos_repack_kernel(const T* __restrict__ u, T* __restrict__ u_aos, int64_t n, int C) {
     const int64_t i = (int64_t)blockIdx.x * ABLOCK + threadIdx.x;
@@ -187,16 +104,6 @@ template <typename T, int N, int W>
 cudaError_t launch_aos(const EvalParams<T>& P, cudaStream_t s) {
     const unsigned nb = (unsigned)((P.n_points + ABLOCK - 1) / ABLOCK);
     const bool narrow = sizeof(T) == 8 && P.coherent_points;   // only 32-byte nodes have two load shapes
-    if (P.coherent_points && !P.use_cached_idx && W >= 3 && getenv("DIND_PAIR")) {   // opt-in until measured
-        const unsigned nbp = (unsigned)(((P.n_points + 1) / 2 + ABLOCK - 1) / ABLOCK);
-        switch (P.n_comp) {
-            case 2: unstructured_aos_pair_kernel<T, N, W, 2, true><<<nbp, ABLOCK, 0, s>>>(P); break;
-            case 3: unstructured_aos_pair_kernel<T, N, W, 3, sizeof(T) != 8><<<nbp, ABLOCK, 0, s>>>(P); break;
-            case 4: unstructured_aos_pair_kernel<T, N, W, 4, sizeof(T) != 8><<<nbp, ABLOCK, 0, s>>>(P); break;
-            default: return cudaErrorInvalidValue;
-        }
-        return cudaGetLastError();
-    }
     switch (P.n_comp) {
         case 2: unstructured_aos_kernel<T, N, W, 2, true><<<nb, ABLOCK, 0, s>>>(P); break;
         case 3:
