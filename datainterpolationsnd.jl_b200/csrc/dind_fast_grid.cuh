@@ -19,6 +19,7 @@
 // slice of the chunk is staged in shared memory (warp-uniform LDS).  Band widths are 2..4:
 // FP32/FP64 FMA pipes, not tensor cores (a per-axis band matrix is >98 % zeros).
 #pragma once
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -30,7 +31,7 @@ namespace {
 
 constexpr int PBLOCK = 128;
 constexpr int PWARPS = PBLOCK / 32;
-constexpr int MAXCHUNK = 64;
+constexpr int MAXCHUNK = 128;
 
 // tuning knob for experiments (not part of the API): DIND_CHUNK=<1..64>
 inline int env_int(const char* name, int dflt) {
@@ -411,6 +412,15 @@ __global__ void __launch_bounds__(PBLOCK, PF ? 5 : ((sizeof(T) == 8 || W >= 3 ||
             const int64_t o = (int64_t)first + omm + C.row0 + (int64_t)ro * C.s1 + seg * EL;
             if (o + (int64_t)(P.dim[N - 1].n_u - 1) * C.sN < P.u_comp_stride) C.pf_off = (int)o;
         }
+        // the chunk's first window and the planes the walk's own prefetch will not ask for
+        if (C.pf_off >= 0) {
+            const int nN = P.dim[N - 1].n_u, i0 = s_i0[0];
+            for (int a = 0; a < W + pf1; ++a) {
+                const int64_t o = C.pf_off + (int64_t)min(i0 + a, nN - 1) * C.sN;
+                prefetch_l1(P.u + o);
+                if (NURBS) prefetch_l1(P.wts + o);
+            }
+        }
     }
     const int64_t R = L.out_stride;              // points per last-axis coordinate
     out_off += (int64_t)g_lo * R;
@@ -433,20 +443,35 @@ cudaError_t launch_pencil_cfg(const EvalParams<T>& P, cudaStream_t s) {
     const int n_last = (int)P.dim[N - 1].n_eval;
     const int bx = (int)((items + PWARPS - 1) / PWARPS);
     // >= ~6 waves of CTAs (short tail) while keeping pencils long enough to amortise the window start-up
-    int chunk = 32;   // measured on config 2: 32 and 64 are within 1 %, 16 and below pay the window start-up
+    // measured on config 2 with the L1 prefetch: 64 -> 0.114 ms, 52 -> 0.116, 32 -> 0.118, 16 -> 0.131 (window
+    // start-up), 86 -> 0.125, 128 -> 0.134 (too few CTAs: 1.4 waves)
+    int chunk = 64;
+    {
+        // ... unless 64 leaves a visibly emptier last wave than 32 (CTAs per SM as in the launch bounds), or there is
+        // no window to start up (W = 1): F64 trilinear 256^3 -> 512^3 3.46 waves vs 6.9: 636 vs 660 Gpoints/s
+        const bool pfk = !P.wts && sizeof(T) == 4 && W == 2;
+        const double slots = 148.0 * (pfk ? 5 : ((sizeof(T) == 8 || W >= 3 || N >= 4) ? 4 : 8));
+        auto fill = [&](int ch) {
+            const double waves = (double)bx * ((n_last + ch - 1) / ch) / slots;
+            return waves / ceil(waves);
+        };
+        if (W == 1 || (fill(64) < 0.9 && fill(32) > fill(64) + 0.05)) chunk = 32;
+    }
     while (chunk > 8 && (int64_t)bx * ((n_last + chunk - 1) / chunk) < 148 * 5 * 2) chunk >>= 1;
     chunk = min(MAXCHUNK, max(1, env_int("DIND_CHUNK", chunk)));
     dim3 grid((unsigned)bx, (unsigned)((n_last + chunk - 1) / chunk));
-    // warm L2 with u when it (plus the NURBS weights) fits comfortably and the pointers allow bulk prefetch
+    // L1 prefetch distance, measured: config 2 0 -> 0.133 ms, 1..3 -> 0.122 ms, 6 -> 0.128 ms; every W = 2 / 3 case
+    // of scripts/sanity_perf.py gains 2-16 %, the W = 4 cases (long runs, 3-4x upsampling) lose 3-6 %
+    constexpr int pf1_default = W <= 3 ? 2 : 0;
+    // warm L2 with u when it (plus the NURBS weights) fits comfortably and the pointers allow bulk prefetch; with the
+    // L1 prefetch running ahead of the walk the warm-up only competes with it (config 2: 0.116 with, 0.114 ms without)
     const size_t u_bytes = (size_t)P.u_comp_stride * (P.n_comp + (P.wts ? 1 : 0)) * sizeof(T);
     int l2_warm = u_bytes >= (1u << 20) && u_bytes <= (96u << 20) && reinterpret_cast<uintptr_t>(P.u) % 16 == 0 &&
                   (!P.wts || reinterpret_cast<uintptr_t>(P.wts) % 16 == 0);
-    l2_warm = env_int("DIND_L2_WARM", l2_warm);
+    l2_warm = env_int("DIND_L2_WARM", l2_warm && pf1_default == 0);
     const bool full = n1 % (32 * VX) == 0 && (N < 3 || P.dim[1].n_eval % J == 0);
     const bool pf = env_int("DIND_PF", 1) != 0;
-    // L1 prefetch distance, measured: config 2 0 -> 0.133 ms, 1..3 -> 0.122 ms, 6 -> 0.128 ms; every W = 2 / 3 case
-    // of scripts/sanity_perf.py gains 2-16 %, the W = 4 cases (long runs, 3-4x upsampling) lose 3-6 %
-    const int pf1 = env_int("DIND_PF1", W <= 3 ? 2 : 0);
+    const int pf1 = env_int("DIND_PF1", pf1_default);
     if (P.wts) {
         if (full) grid_pencil_kernel<T, N, W, VX, J, true, true, false><<<grid, PBLOCK, 0, s>>>(P, (int)items, nseg, n2g, chunk, l2_warm, pf1);
         else grid_pencil_kernel<T, N, W, VX, J, true, false, false><<<grid, PBLOCK, 0, s>>>(P, (int)items, nseg, n2g, chunk, l2_warm, pf1);
