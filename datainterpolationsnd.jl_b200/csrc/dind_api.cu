@@ -194,8 +194,8 @@ int upload_dim(dind_interp_s* h, DimState& D) {
         const T t0 = kn[0];
         const T scale = T(nb) / (kn[n - 1] - kn[0]);
         if (std::isfinite((double)scale) && scale > T(0)) {
-            CUDA_TRY(D.d_lut.ensure((size_t)(nb + 1) * sizeof(int32_t)));
-            CUDA_TRY(launch_lut<T>((const T*)D.d_knots.p, n, t0, scale, nb, (int32_t*)D.d_lut.p, h->stream));
+            CUDA_TRY(D.d_lut.ensure((size_t)nb * sizeof(int2)));
+            CUDA_TRY(launch_lut<T>((const T*)D.d_knots.p, n, t0, scale, nb, (int2*)D.d_lut.p, h->stream));
             D.lut_n = nb;
             D.lut_t0 = (double)t0;
             D.lut_scale = (double)scale;
@@ -218,7 +218,7 @@ DimParams<T> make_dim_params(const dind_interp_s* h, const DimState& D, int dim,
     P.tab_i0 = (const int32_t*)D.table.i0.p;
     P.tab_w = (const T*)D.table.w.p;
     P.tab_flag = (const uint8_t*)D.table.flag.p;
-    P.lut = D.lut_n ? (const int32_t*)D.d_lut.p : nullptr;
+    P.lut = D.lut_n ? (const int2*)D.d_lut.p : nullptr;
     P.lut_t0 = (T)D.lut_t0;
     P.lut_scale = (T)D.lut_scale;
     P.lut_n = D.lut_n;

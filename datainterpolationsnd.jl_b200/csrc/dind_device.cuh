@@ -21,8 +21,8 @@ enum Kind : int { LINEAR = 0, CONSTANT = 1, BSPLINE = 2 };
 // ---- Julia `isless` total order via sortable integer keys -------------------------------
 // key(a) < key(b)  <=>  isless(a, b):  -0.0 < +0.0, every NaN is the greatest element.
 template <typename T> struct KeyOf;
-template <> struct KeyOf<float> { using type = int32_t; };
-template <> struct KeyOf<double> { using type = int64_t; };
+template <> struct KeyOf<float> { using type = int32_t; static constexpr int32_t nan = 0x7fffffff; };
+template <> struct KeyOf<double> { using type = int64_t; static constexpr int64_t nan = 0x7fffffffffffffffLL; };
 
 __host__ __device__ __forceinline__ int32_t to_key(float v) {
 #ifdef __CUDA_ARCH__
@@ -82,13 +82,22 @@ __device__ __forceinline__ int lut_bucket(T x, T t0, T scale, int n_buckets) {
 
 template <typename K, bool LE>
 __device__ __forceinline__ int count_range(const K* __restrict__ keys, int lo, int hi, K kx) {
-    int cnt = lo;
     const int len = hi - lo;
-    if (len > 0) {
-        for (int step = 1 << (31 - __clz(len)); step > 0; step >>= 1) {
-            const int j = cnt + step;
-            if (j <= hi && (LE ? keys[j - 1] <= kx : keys[j - 1] < kx)) cnt = j;
-        }
+    if (len <= 2) {
+        // the usual case (~4 buckets per knot), branch-free: the keys are sorted, so the count over the one or
+        // two candidates is a prefix of passed comparisons.  lo < n whenever len > 0.
+        const int j0 = max(lo - (int)(len <= 0), 0);   // any valid address when there is no candidate (lo may be n)
+        const int j1 = len == 2 ? lo + 1 : j0;
+        const K k0 = __ldg(keys + j0);
+        const K k1 = __ldg(keys + j1);
+        const bool p0 = len >= 1 && (LE ? k0 <= kx : k0 < kx);
+        const bool p1 = len == 2 && (LE ? k1 <= kx : k1 < kx);
+        return lo + (int)p0 + (int)(p0 && p1);
+    }
+    int cnt = lo;
+    for (int step = 1 << (31 - __clz(len)); step > 0; step >>= 1) {
+        const int j = cnt + step;
+        if (j <= hi && (LE ? keys[j - 1] <= kx : keys[j - 1] < kx)) cnt = j;
     }
     return cnt;
 }
@@ -117,8 +126,9 @@ struct DimParams {
     int32_t n_u;           // size(u, dim)
     int32_t order;         // derivative order requested for this dimension
     // bucket table accelerating the interval search (null = plain binary search): for bucket
-    // b = lut_bucket(x), count_lt(x) and count_le(x) lie in [lut[b], lut[b + 1]]
-    const int32_t* lut;
+    // b = lut_bucket(x), count_lt(x) and count_le(x) lie in [lut[b].x, lut[b].y] (.y = the next bucket's .x;
+    // stored as pairs so that a query is ONE 8-byte load)
+    const int2* lut;
     T lut_t0, lut_scale;
     int32_t lut_n;
 };
@@ -166,10 +176,9 @@ __device__ __forceinline__ int dim_count(const DimParams<T>& D, T x, typename Ke
     using K = typename KeyOf<T>::type;
     const int n = D.n_knots;
     if (D.lut == nullptr) return LE ? count_le(D.keys, n, kx) : count_lt(D.keys, n, kx);
-    if (kx == to_key(T(0) / T(0))) return n;   // NaN sorts after every knot
-    const int b = lut_bucket(x, D.lut_t0, D.lut_scale, D.lut_n);
-    const int lo = __ldg(D.lut + b), hi = __ldg(D.lut + b + 1);
-    return count_range<K, LE>(D.keys, lo, hi, kx);
+    if (kx == KeyOf<T>::nan) return n;   // NaN sorts after every knot
+    const int2 r = __ldg(D.lut + lut_bucket(x, D.lut_t0, D.lut_scale, D.lut_n));
+    return count_range<K, LE>(D.keys, r.x, r.y, kx);
 }
 
 // ---- Cox–de Boor in registers (src/spline_utils.jl:24-114), runtime degree ---------------

@@ -7,6 +7,8 @@
 // fetches).  The handle keeps a repacked copy u_aos[c + C*i] (one extra pass per dind_set_u, SURVEY.md
 // §7.2 "repack allowed"): all components of a node are ONE 8/16/32-byte vector load (3-component nodes are
 // padded to 4 so that a node never straddles a 32-byte sector).  Outputs keep the reference's layout (n_points, out...).
+#include <cstdlib>
+
 #include "dind_kernels.h"
 
 namespace dind {
@@ -65,8 +67,8 @@ __device__ __forceinline__ int stencil_ct(const DimParams<T>& D, T x, int cached
     return idx - W;
 }
 
-template <typename T, int N, int W, int C, bool WIDE>
-__global__ void __launch_bounds__(ABLOCK) unstructured_aos_kernel(const __grid_constant__ EvalParams<T> P) {
+template <typename T, int N, int W, int C, bool WIDE, int MINB = 0>
+__global__ void __launch_bounds__(ABLOCK, MINB) unstructured_aos_kernel(const __grid_constant__ EvalParams<T> P) {
     const int64_t k = (int64_t)blockIdx.x * ABLOCK + threadIdx.x;
     if (k >= P.n_points) return;
     constexpr int S = C == 3 ? 4 : C;   // aos_node_stride(C)
@@ -107,6 +109,10 @@ cudaError_t launch_aos(const EvalParams<T>& P, cudaStream_t s) {
     switch (P.n_comp) {
         case 2: unstructured_aos_kernel<T, N, W, 2, true><<<nb, ABLOCK, 0, s>>>(P); break;
         case 3:
+            // config 3 in plan order: asking for 4 CTAs/SM (64 registers instead of the 60 ptxas picks on its own)
+            // changes the schedule: 1.43 -> 1.33 ms; 3 CTAs (80 registers) 1.49, 5 (48) 1.36, 6 (40, spills) 1.58
+            if (narrow && W == 4 && N == 3) unstructured_aos_kernel<T, N, W, 3, sizeof(T) != 8, 4><<<nb, ABLOCK, 0, s>>>(P);
+            else
             if (narrow) unstructured_aos_kernel<T, N, W, 3, sizeof(T) != 8><<<nb, ABLOCK, 0, s>>>(P);
             else unstructured_aos_kernel<T, N, W, 3, true><<<nb, ABLOCK, 0, s>>>(P);
             break;

@@ -56,16 +56,20 @@ __global__ void __launch_bounds__(BLOCK) axis_table_kernel(DimParams<T> D, int o
 }
 
 template <typename T>
-__global__ void __launch_bounds__(BLOCK) lut_kernel(const T* __restrict__ knots, int n, T t0, T scale, int nb, int32_t* __restrict__ lut) {
+__global__ void __launch_bounds__(BLOCK) lut_kernel(const T* __restrict__ knots, int n, T t0, T scale, int nb, int2* __restrict__ lut) {
     const int b = blockIdx.x * BLOCK + threadIdx.x;
-    if (b > nb) return;
-    // first knot whose bucket is >= b (buckets are non-decreasing along the sorted knots)
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int m = (lo + hi) >> 1;
-        if (lut_bucket(knots[m], t0, scale, nb) < b) lo = m + 1; else hi = m;
+    if (b >= nb) return;
+    // first knot whose bucket is >= b, and >= b + 1 (buckets are non-decreasing along the sorted knots)
+    int first[2];
+    for (int q = 0; q < 2; ++q) {
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            const int m = (lo + hi) >> 1;
+            if (lut_bucket(knots[m], t0, scale, nb) < b + q) lo = m + 1; else hi = m;
+        }
+        first[q] = lo;
     }
-    lut[b] = lo;
+    lut[b] = make_int2(first[0], first[1]);
 }
 
 template <typename T>
@@ -182,8 +186,8 @@ cudaError_t launch_axis_table(const DimParams<T>& D, int order, int32_t* tab_i0,
 }
 
 template <typename T>
-cudaError_t launch_lut(const T* knots, int n_knots, T t0, T scale, int n_buckets, int32_t* lut, cudaStream_t s) {
-    lut_kernel<T><<<blocks_for(n_buckets + 1, BLOCK), BLOCK, 0, s>>>(knots, n_knots, t0, scale, n_buckets, lut);
+cudaError_t launch_lut(const T* knots, int n_knots, T t0, T scale, int n_buckets, int2* lut, cudaStream_t s) {
+    lut_kernel<T><<<blocks_for(n_buckets, BLOCK), BLOCK, 0, s>>>(knots, n_knots, t0, scale, n_buckets, lut);
     return cudaGetLastError();
 }
 
@@ -204,7 +208,7 @@ cudaError_t launch_eval_generic(const EvalParams<T>& P, bool grid, cudaStream_t 
 }
 
 #define DIND_INSTANTIATE(T)                                                                                    \
-    template cudaError_t launch_lut<T>(const T*, int, T, T, int, int32_t*, cudaStream_t);                      \
+    template cudaError_t launch_lut<T>(const T*, int, T, T, int, int2*, cudaStream_t);                         \
     template cudaError_t launch_idx<T>(const DimParams<T>&, int32_t*, cudaStream_t);                          \
     template cudaError_t launch_basis_cache<T>(const DimParams<T>&, int, T*, cudaStream_t);                   \
     template cudaError_t launch_axis_table<T>(const DimParams<T>&, int, int32_t*, T*, uint8_t*, cudaStream_t); \

@@ -13,7 +13,7 @@ template <typename T> cudaError_t launch_basis_cache(const DimParams<T>& D, int 
 template <typename T> cudaError_t launch_axis_table(const DimParams<T>& D, int order, int32_t* tab_i0, T* tab_w,
                                                     uint8_t* tab_flag, cudaStream_t s);
 // bucket table of the interval search: lut[b] = #{i : lut_bucket(knots[i]) < b}, b = 0..n_buckets
-template <typename T> cudaError_t launch_lut(const T* knots, int n_knots, T t0, T scale, int n_buckets, int32_t* lut, cudaStream_t s);
+template <typename T> cudaError_t launch_lut(const T* knots, int n_knots, T t0, T scale, int n_buckets, int2* lut, cudaStream_t s);
 // uw[i + c*n] = u[i + c*n] * w[i]  (NURBS numerator, src/interpolation_methods.jl:124-131)
 template <typename T> cudaError_t launch_premultiply(const T* u, const T* w, T* uw, int64_t n, int n_comp, cudaStream_t s);
 // generic evaluation: any N_in <= MAXN, any kinds, any degree <= MAXW-1
