@@ -120,7 +120,8 @@ struct dind_interp_s {
     // cell-sorted plan for eval_unstructured (dind_plan.cu)
     bool plan_valid = false;
     int64_t plan_n = 0;
-    DevBuf plan_perm, plan_stage, plan_scratch, plan_slot2, plan_dest2;
+    DevBuf plan_perm, plan_stage, plan_scratch, plan_slot2, plan_dest2, plan_cells;
+    bool plan_has_cells = false;   // plan_cells holds the packed cell words of the current plan
     bool plan_buckets_valid = false;
     DevBuf plan_t[MAXN];
     // staging
@@ -414,7 +415,23 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     if (!grid && have_idx_cache && (flags & DIND_FLAG_CELL_SORTED)) {
         if (n_points >= (1LL << 32) || h->comp_stride >= (1LL << 32))
             return fail(DIND_ERR_UNSUPPORTED, "DIND_FLAG_CELL_SORTED needs fewer than 2^32 points and u elements per component");
+        // packed cell words: every dimension's first node in its own bit field of one 32-bit word, when they fit
+        // (Linear / BSpline dimensions; a Constant dimension's node is not its interval index)
+        int cell_bits = 0;
+        for (int d = 0; d < N && cell_bits >= 0; ++d) {
+            if (P.dim[d].kind == CONSTANT || getenv("DIND_NO_CELLS")) { cell_bits = -1; break; }
+            int b = 1;
+            while ((1 << b) < P.dim[d].n_u) ++b;
+            P.dim[d].cell_shift = cell_bits;
+            P.dim[d].cell_mask = (1 << b) - 1;
+            P.dim[d].cell_add = P.dim[d].kind == LINEAR ? 1 : P.dim[d].width;
+            cell_bits += b;
+            if (cell_bits > 32) cell_bits = -1;
+        }
         if (!h->plan_valid || h->plan_n != n_points) {
+            h->plan_has_cells = cell_bits > 0 && h->plan_cells.ensure((size_t)n_points * sizeof(uint32_t)) == cudaSuccess;
+            if (!h->plan_has_cells) (void)cudaGetLastError();
+            uint32_t* cells = h->plan_has_cells ? (uint32_t*)h->plan_cells.p : nullptr;
             CUDA_TRY(h->plan_perm.ensure((size_t)n_points * sizeof(uint32_t)));
             T* ts[MAXN];
             for (int d = 0; d < N; ++d) {
@@ -422,13 +439,13 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
                 ts[d] = (T*)h->plan_t[d].p;
             }
             size_t scratch_bytes = 0;
-            CUDA_TRY(plan_sort_points<T>(P, nullptr, ts, nullptr, &scratch_bytes, h->stream));
+            CUDA_TRY(plan_sort_points<T>(P, nullptr, ts, cells, cell_bits, nullptr, &scratch_bytes, h->stream));
             // sort scratch (keys in/out, values in, CUB temp) stays with the handle: a new t_eval of the same
             // size re-plans without cudaMalloc / cudaFree (which would also synchronise the device)
             size_t sb2 = 0;   // the un-permutation schedule sorts in the same scratch later
             CUDA_TRY(plan_bucket_schedule(nullptr, nullptr, nullptr, n_points, nullptr, &sb2, h->stream));
             CUDA_TRY(h->plan_scratch.ensure(std::max(scratch_bytes, sb2)));
-            CUDA_TRY(plan_sort_points<T>(P, (uint32_t*)h->plan_perm.p, ts, h->plan_scratch.p, &scratch_bytes, h->stream));
+            CUDA_TRY(plan_sort_points<T>(P, (uint32_t*)h->plan_perm.p, ts, cells, cell_bits, h->plan_scratch.p, &scratch_bytes, h->stream));
             h->launches += 2 + N;
             h->plan_valid = true;
             h->plan_buckets_valid = false;
@@ -440,6 +457,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         }
         P.use_cached_idx = 0;
         P.coherent_points = 1;
+        P.cells = (h->plan_has_cells && cell_bits > 0) ? (const uint32_t*)h->plan_cells.p : nullptr;
         P.perm = (flags & DIND_FLAG_PLAN_ORDER) ? nullptr : (const uint32_t*)h->plan_perm.p;
         // Results go back to their original positions in two levels (dind_plan.cu): the kernel writes each
         // result as one aligned record to a staging slot ordered by the 2048-point window of its destination,
@@ -677,7 +695,7 @@ int dind_destroy(dind_handle_t h) {
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_kernel) cudaEventDestroy(h->ev_kernel);
     for (int i = 0; i < 2; ++i) if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
-    h->plan_perm.release(); h->plan_stage.release(); h->plan_scratch.release(); h->plan_slot2.release(); h->plan_dest2.release();
+    h->plan_perm.release(); h->plan_stage.release(); h->plan_scratch.release(); h->plan_slot2.release(); h->plan_dest2.release(); h->plan_cells.release();
     for (int d = 0; d < MAXN; ++d) h->plan_t[d].release();
     delete h;
     return DIND_OK;

@@ -131,6 +131,10 @@ struct DimParams {
     const int2* lut;
     T lut_t0, lut_scale;
     int32_t lut_n;
+    // cell-sorted plan with packed cells (EvalParams::cells): this dimension's first stencil node sits in bits
+    // [cell_shift, cell_shift + popc(cell_mask)) of the point's cell word; cell_add turns it into the reference's
+    // 1-based idx (Linear: + 1, BSpline: + degree + 1)
+    int32_t cell_shift, cell_mask, cell_add;
 };
 
 template <typename T>
@@ -151,6 +155,8 @@ struct EvalParams {
     int32_t zero_result;   // Linear with order > 1 somewhere: result is identically zero
     int32_t use_cached_idx;
     const uint32_t* perm;  // cell-sorted plan: output position of point k of the (sorted) t_eval arrays; null = identity
+    const uint32_t* cells; // cell-sorted plan: per plan position the packed first stencil nodes of all dimensions (the
+                           // plan's sort key, kept): the kernels decode the interval instead of searching; null = search
     int32_t n_stencil;       // grid: > 0 = dim[0..n_stencil) are the stencil axes and the rest identity/selector ("point") axes,
                              // already in kernel order (dind_fast_grid_split.cu); 0 = let the dispatcher classify the axes
     int32_t u_is_raw;        // NURBS: u has NOT been pre-multiplied by the weights (only the split grid path accepts that)
@@ -179,6 +185,12 @@ __device__ __forceinline__ int dim_count(const DimParams<T>& D, T x, typename Ke
     if (kx == KeyOf<T>::nan) return n;   // NaN sorts after every knot
     const int2 r = __ldg(D.lut + lut_bucket(x, D.lut_t0, D.lut_scale, D.lut_n));
     return count_range<K, LE>(D.keys, r.x, r.y, kx);
+}
+
+// the reference's 1-based idx of dimension D from the plan's packed cell word
+template <typename T>
+__device__ __forceinline__ int cell_idx(const DimParams<T>& D, uint32_t cell) {
+    return (int)((cell >> D.cell_shift) & (uint32_t)D.cell_mask) + D.cell_add;
 }
 
 // ---- Cox–de Boor in registers (src/spline_utils.jl:24-114), runtime degree ---------------

@@ -97,18 +97,18 @@ struct ContractGV<T, 0, W, C, WIDE> {
 
 // order-0 and order-1 stencil weights of one dimension (compile-time width)
 template <typename T, int W>
-__device__ __forceinline__ int stencil_w_dw(const DimParams<T>& D, T x, T (&w)[W], T (&dw)[W]) {
+__device__ __forceinline__ int stencil_w_dw(const DimParams<T>& D, T x, int cached_idx, T (&w)[W], T (&dw)[W]) {
     using K = typename KeyOf<T>::type;
     const K kx = to_key(x);
     const int n = D.n_knots;
     if (W == 2 && D.kind == LINEAR) {
-        const int c = clampi(dim_count<T, false>(D, x, kx), 1, n - 1) - 1;
+        const int c = (cached_idx ? cached_idx : clampi(dim_count<T, false>(D, x, kx), 1, n - 1)) - 1;
         const T t1 = __ldg(D.knots + c), t2 = __ldg(D.knots + c + 1), r = __ldg(D.recip + c);
         w[0] = (t2 - x) * r; w[1] = (x - t1) * r;
         dw[0] = -r; dw[1] = r;
         return c;
     }
-    const int idx = clampi(dim_count<T, true>(D, x, kx), W, n - W);
+    const int idx = cached_idx ? cached_idx : clampi(dim_count<T, true>(D, x, kx), W, n - W);
     bspline_basis_ct<T, W - 1>(D.knots, D.recip, n, idx - 1, x, 0, w);
     bspline_basis_ct<T, W - 1>(D.knots, D.recip, n, idx - 1, x, 1, dw);
     return idx - W;
@@ -121,10 +121,11 @@ __global__ void __launch_bounds__(GBLOCK) unstructured_gradient_kernel(const __g
     T w[MAXN][W], dw[MAXN][W];
     int stride[MAXN];
     int64_t base = 0;
+    const uint32_t cell = P.cells ? __ldcs(P.cells + k) : 0u;
 #pragma unroll
     for (int d = 0; d < N; ++d) {
         const DimParams<T>& D = P.dim[d];
-        const int i0 = stencil_w_dw<T, W>(D, __ldcs(D.t_eval + k), w[d], dw[d]);
+        const int i0 = stencil_w_dw<T, W>(D, __ldcs(D.t_eval + k), P.cells ? cell_idx<T>(D, cell) : 0, w[d], dw[d]);
         stride[d] = (int)D.u_stride;
         base += (int64_t)i0 * D.u_stride;
     }
@@ -146,10 +147,11 @@ __global__ void __launch_bounds__(GBLOCK, 2) unstructured_gradient_aos_kernel(co
     T w[MAXN][W], dw[MAXN][W];
     int stride[MAXN];
     int64_t base = 0;
+    const uint32_t cell = P.cells ? __ldcs(P.cells + k) : 0u;
 #pragma unroll
     for (int d = 0; d < N; ++d) {
         const DimParams<T>& D = P.dim[d];
-        const int i0 = stencil_w_dw<T, W>(D, __ldcs(D.t_eval + k), w[d], dw[d]);
+        const int i0 = stencil_w_dw<T, W>(D, __ldcs(D.t_eval + k), P.cells ? cell_idx<T>(D, cell) : 0, w[d], dw[d]);
         stride[d] = (int)D.u_stride * S;
         base += (int64_t)i0 * D.u_stride;
     }

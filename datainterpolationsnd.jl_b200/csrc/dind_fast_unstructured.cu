@@ -65,11 +65,12 @@ __global__ void __launch_bounds__(UBLOCK) unstructured_kernel(const __grid_const
     T w[MAXN][W];
     int stride[MAXN];
     int64_t base = 0;
+    const uint32_t cell = P.cells ? __ldcs(P.cells + k) : 0u;
 #pragma unroll
     for (int d = 0; d < N; ++d) {
         const DimParams<T>& D = P.dim[d];
         const T x = __ldcs(D.t_eval + k);
-        const int cached = P.use_cached_idx ? __ldcs(D.idx_eval + k) : 0;
+        const int cached = P.cells ? cell_idx<T>(D, cell) : (P.use_cached_idx ? __ldcs(D.idx_eval + k) : 0);
         const int i0 = stencil_ct<T, W>(D, x, cached, w[d]);
         stride[d] = (int)D.u_stride;
         base += (int64_t)i0 * D.u_stride;

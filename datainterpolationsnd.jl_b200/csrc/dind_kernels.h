@@ -21,11 +21,12 @@ template <typename T> cudaError_t launch_eval_generic(const EvalParams<T>& P, bo
 
 // Cell-sorted plan for eval_unstructured (dind_plan.cu): perm = point indices sorted by the
 // offset of their first stencil node in u (points of one cell become neighbours, cells follow
-// memory order), t_sorted[d] = t_eval[d][perm].  scratch_bytes in/out: pass *scratch = nullptr to
-// query the scratch size.
+// memory order), t_sorted[d] = t_eval[d][perm].  cells != nullptr: the sort key is the packed per-dimension
+// first nodes (DimParams::cell_shift, cell_bits bits in all) and the sorted keys are kept in cells[].
+// scratch_bytes in/out: pass *scratch = nullptr to query the scratch size.
 template <typename T>
-cudaError_t plan_sort_points(const EvalParams<T>& P, uint32_t* perm, T* const* t_sorted, void* scratch,
-                             size_t* scratch_bytes, cudaStream_t s);
+cudaError_t plan_sort_points(const EvalParams<T>& P, uint32_t* perm, T* const* t_sorted, uint32_t* cells, int cell_bits,
+                             void* scratch, size_t* scratch_bytes, cudaStream_t s);
 
 // Component-fastest repack of u for vector-valued unstructured evaluation (dind_fast_unstructured_aos.cu).
 // elements per node of the component-fastest copy: 3 components are padded to 4 (one aligned vector per node)

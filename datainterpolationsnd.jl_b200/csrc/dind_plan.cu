@@ -19,7 +19,10 @@ namespace {
 
 constexpr int BLOCK = 256;
 
-template <typename T>
+// PACKED: the key is the per-dimension first nodes in bit fields (last dimension most significant: the same
+// order as the offset in u) — kept after the sort as the plan's cell words, which the evaluation kernels decode
+// instead of searching again.
+template <typename T, bool PACKED>
 __global__ void __launch_bounds__(BLOCK) plan_key_kernel(const __grid_constant__ EvalParams<T> P, uint32_t* __restrict__ keys,
                                                          uint32_t* __restrict__ vals) {
     const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -27,7 +30,9 @@ __global__ void __launch_bounds__(BLOCK) plan_key_kernel(const __grid_constant__
     int64_t base = 0;
     for (int d = 0; d < P.n_in; ++d) {
         const DimParams<T>& D = P.dim[d];
-        base += (int64_t)dim_first_node<T>(D, __ldcs(D.t_eval + k)) * D.u_stride;
+        const int i0 = dim_first_node<T>(D, __ldcs(D.t_eval + k));
+        if (PACKED) base |= (int64_t)i0 << D.cell_shift;
+        else base += (int64_t)i0 * D.u_stride;
     }
     keys[k] = (uint32_t)base;
     vals[k] = (uint32_t)k;
@@ -156,11 +161,12 @@ template cudaError_t plan_unbucket<float>(const float*, const uint32_t*, float*,
 template cudaError_t plan_unbucket<double>(const double*, const uint32_t*, double*, int64_t, int, int, cudaStream_t);
 
 template <typename T>
-cudaError_t plan_sort_points(const EvalParams<T>& P, uint32_t* perm, T* const* t_sorted, void* scratch,
-                             size_t* scratch_bytes, cudaStream_t s) {
+cudaError_t plan_sort_points(const EvalParams<T>& P, uint32_t* perm, T* const* t_sorted, uint32_t* cells, int cell_bits,
+                             void* scratch, size_t* scratch_bytes, cudaStream_t s) {
     const int64_t n = P.n_points;
     int end_bit = 1;
     while (end_bit < 32 && (1LL << end_bit) < P.u_comp_stride) ++end_bit;
+    if (cells) end_bit = cell_bits;
     size_t cub_bytes = 0;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                                     (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, end_bit, s);
@@ -178,9 +184,10 @@ cudaError_t plan_sort_points(const EvalParams<T>& P, uint32_t* perm, T* const* t
     uint32_t* vals_in = (uint32_t*)(base + 2 * arr);
     void* cub_tmp = base + 3 * arr;
     const unsigned nb = (unsigned)((n + BLOCK - 1) / BLOCK);
-    plan_key_kernel<T><<<nb, BLOCK, 0, s>>>(P, keys_in, vals_in);
+    if (cells) plan_key_kernel<T, true><<<nb, BLOCK, 0, s>>>(P, keys_in, vals_in);
+    else plan_key_kernel<T, false><<<nb, BLOCK, 0, s>>>(P, keys_in, vals_in);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    e = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, keys_out, vals_in, perm, n, 0, end_bit, s);
+    e = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, cells ? cells : keys_out, vals_in, perm, n, 0, end_bit, s);
     if (e != cudaSuccess) return e;
     for (int d = 0; d < P.n_in; ++d) {
         plan_gather_kernel<T><<<nb, BLOCK, 0, s>>>(P.dim[d].t_eval, perm, t_sorted[d], n);
@@ -189,7 +196,7 @@ cudaError_t plan_sort_points(const EvalParams<T>& P, uint32_t* perm, T* const* t
     return cudaSuccess;
 }
 
-template cudaError_t plan_sort_points<float>(const EvalParams<float>&, uint32_t*, float* const*, void*, size_t*, cudaStream_t);
-template cudaError_t plan_sort_points<double>(const EvalParams<double>&, uint32_t*, double* const*, void*, size_t*, cudaStream_t);
+template cudaError_t plan_sort_points<float>(const EvalParams<float>&, uint32_t*, float* const*, uint32_t*, int, void*, size_t*, cudaStream_t);
+template cudaError_t plan_sort_points<double>(const EvalParams<double>&, uint32_t*, double* const*, uint32_t*, int, void*, size_t*, cudaStream_t);
 
 }  // namespace dind

@@ -571,6 +571,33 @@ def test_cell_sorted_plan_is_bit_identical(D, dtype, case):
     itp.close()
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", [1, 2, 3, 7, 9, 12])
+def test_cell_sorted_plan_packed_cells_and_search_agree(D, dtype, case, monkeypatch):
+    """The plan keeps its sort key — the per-dimension first nodes packed into one word — and the kernels decode
+    the interval from it instead of searching; with DIND_NO_CELLS the plan sorts by the offset in u and the
+    kernels search.  Same bits either way (value, derivative, fused gradient), equal to the unsorted result."""
+    kinds, degrees, n_knots, out_dims, _ = CASES[case]
+    rng = np.random.default_rng(900 + case)
+    ts, u, _ = _case(rng, kinds, degrees, n_knots, out_dims, dtype)
+    xs = H.zipped_queries(rng, ts, 30011, dtype)
+    mk = lambda: D.NDInterpolation(u, H.make_dims(D, kinds, ts, xs, degrees, None, max_deriv=[1] * len(kinds)))
+    a, b, c = mk(), mk(), mk()
+    orders = (1,) + (0,) * (len(kinds) - 1)
+    ref = [D.eval_unstructured(a), D.eval_unstructured(a, derivative_orders=orders), D.eval_unstructured_gradient(a)]
+    got = [D.eval_unstructured(b, flags=CELL_SORTED), D.eval_unstructured(b, derivative_orders=orders, flags=CELL_SORTED),
+           D.eval_unstructured_gradient(b, flags=CELL_SORTED)]
+    monkeypatch.setenv("DIND_NO_CELLS", "1")
+    alt = [D.eval_unstructured(c, flags=CELL_SORTED), D.eval_unstructured(c, derivative_orders=orders, flags=CELL_SORTED),
+           D.eval_unstructured_gradient(c, flags=CELL_SORTED)]
+    monkeypatch.delenv("DIND_NO_CELLS")
+    for r, g, l in zip(ref, got, alt):
+        assert np.array_equal(r, g, equal_nan=True) and np.array_equal(r, l, equal_nan=True)
+    assert np.array_equal(b.plan_permutation(), c.plan_permutation())   # same cell order from both keys
+    for i in (a, b, c):
+        i.close()
+
+
 def test_nurbs_weights_with_constant_axis(D):
     """BASELINE config 4 names NURBS weights with mixed Constant(left=true)/BSpline dimensions: no
     reference semantics — defined as the tensor product of the per-dimension stencils
