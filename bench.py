@@ -499,17 +499,19 @@ def run_reference(args, wl, rank, world):
     if rank != 0:
         return None
     nthreads = host_threads()   # all host cores, whatever OMP_NUM_THREADS torchrun exported
-    vals = []
+    from oracle import oracle as O
+    vals, secs = [], []
     sample = ""
     for i in range(args.warmup + args.steps):
         v, _, sample = cpu_sample(wl, seconds_target=max(3.0, 60.0 / (args.warmup + args.steps)), nthreads=nthreads)
         if i >= args.warmup:
             vals.append(v)
+            secs.append(O.last_eval_seconds())   # the step = one evaluation of the bounded sample
     value = float(np.mean(vals))
     return {
         "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": "Gpoints/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": wl.dtype_name, "data": "synthetic",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * float(np.mean(secs)), 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype_name, "data": "synthetic",
         "config": {"workload": wl.name, "note": "CPU restatement of the reference (oracle/, C++/OpenMP), not Julia: Julia is not in this image"},
         "cpu_baseline": {"value": round(value, 5), "unit": "Gpoints/s", "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 5), "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
