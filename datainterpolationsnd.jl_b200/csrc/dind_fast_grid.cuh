@@ -252,7 +252,7 @@ __device__ __forceinline__ void walk_pencil(const EvalParams<T>& P, const Pencil
 // One warp = one work item: 32*VX consecutive g_1 x J consecutive g_2 at fixed middle axes,
 // over `chunk` coordinates of the last axis.
 template <typename T, int N, int W, int VX, int J, bool NURBS, bool FULL, bool PF>
-__global__ void __launch_bounds__(PBLOCK, PF ? 5 : ((sizeof(T) == 8 || W >= 3 || N >= 4) ? 4 : 8)) grid_pencil_kernel(const __grid_constant__ EvalParams<T> P, int n_items, int nseg,
+__global__ void __launch_bounds__(PBLOCK, PF ? 4 : ((sizeof(T) == 8 || W >= 3 || N >= 4) ? 4 : 8)) grid_pencil_kernel(const __grid_constant__ EvalParams<T> P, int n_items, int nseg,
                                                              int n2g, int chunk, int l2_warm, int pf1) {
     using Ctx = PencilCtx<T, N, W, VX, J>;
     __shared__ int s_i0[MAXCHUNK];
@@ -450,7 +450,7 @@ cudaError_t launch_pencil_cfg(const EvalParams<T>& P, cudaStream_t s) {
         // ... unless 64 leaves a visibly emptier last wave than 32 (CTAs per SM as in the launch bounds), or there is
         // no window to start up (W = 1): F64 trilinear 256^3 -> 512^3 3.46 waves vs 6.9: 636 vs 660 Gpoints/s
         const bool pfk = !P.wts && sizeof(T) == 4 && W == 2;
-        const double slots = 148.0 * (pfk ? 5 : ((sizeof(T) == 8 || W >= 3 || N >= 4) ? 4 : 8));
+        const double slots = 148.0 * ((pfk || sizeof(T) == 8 || W >= 3 || N >= 4) ? 4 : 8);
         auto fill = [&](int ch) {
             const double waves = (double)bx * ((n_last + ch - 1) / ch) / slots;
             return waves / ceil(waves);
