@@ -122,14 +122,17 @@ __global__ void __launch_bounds__(GBLOCK) unstructured_gradient_kernel(const __g
     int stride[MAXN];
     int64_t base = 0;
     const uint32_t cell = P.cells ? __ldcs(P.cells + k) : 0u;
+    T xs[N];   // all streaming inputs requested up front (see dind_fast_unstructured_aos.cu)
+#pragma unroll
+    for (int d = 0; d < N; ++d) xs[d] = __ldcs(P.dim[d].t_eval + k);
+    const int64_t ko = P.perm ? (int64_t)__ldcs(P.perm + k) : k;
 #pragma unroll
     for (int d = 0; d < N; ++d) {
         const DimParams<T>& D = P.dim[d];
-        const int i0 = stencil_w_dw<T, W>(D, __ldcs(D.t_eval + k), P.cells ? cell_idx<T>(D, cell) : 0, w[d], dw[d]);
+        const int i0 = stencil_w_dw<T, W>(D, xs[d], P.cells ? cell_idx<T>(D, cell) : 0, w[d], dw[d]);
         stride[d] = (int)D.u_stride;
         base += (int64_t)i0 * D.u_stride;
     }
-    const int64_t ko = P.perm ? (int64_t)__ldcs(P.perm + k) : k;
     const int64_t slot = P.out_comp_stride * P.n_comp;   // elements per (value | derivative) block
     for (int c = 0; c < P.n_comp; ++c) {
         const GVec<T, N + 1> g = ContractG<T, N - 1, W>::run(P.u + (int64_t)c * P.u_comp_stride + base, w, dw, stride);
@@ -148,14 +151,17 @@ __global__ void __launch_bounds__(GBLOCK, 2) unstructured_gradient_aos_kernel(co
     int stride[MAXN];
     int64_t base = 0;
     const uint32_t cell = P.cells ? __ldcs(P.cells + k) : 0u;
+    T xs[N];   // all streaming inputs requested up front (see dind_fast_unstructured_aos.cu)
+#pragma unroll
+    for (int d = 0; d < N; ++d) xs[d] = __ldcs(P.dim[d].t_eval + k);
+    const int64_t ko = P.perm ? (int64_t)__ldcs(P.perm + k) : k;
 #pragma unroll
     for (int d = 0; d < N; ++d) {
         const DimParams<T>& D = P.dim[d];
-        const int i0 = stencil_w_dw<T, W>(D, __ldcs(D.t_eval + k), P.cells ? cell_idx<T>(D, cell) : 0, w[d], dw[d]);
+        const int i0 = stencil_w_dw<T, W>(D, xs[d], P.cells ? cell_idx<T>(D, cell) : 0, w[d], dw[d]);
         stride[d] = (int)D.u_stride * S;
         base += (int64_t)i0 * D.u_stride;
     }
-    const int64_t ko = P.perm ? (int64_t)__ldcs(P.perm + k) : k;
     const int64_t slot = P.out_comp_stride * C;
     const GVec<T, (N + 1) * C> g = ContractGV<T, N - 1, W, C, WIDE>::run(P.u_aos + base * S, w, dw, stride);
     T* o = P.out + ko * P.out_point_stride;

@@ -65,11 +65,16 @@ __global__ void __launch_bounds__(UBLOCK) unstructured_kernel(const __grid_const
     T w[MAXN][W];
     int stride[MAXN];
     int64_t base = 0;
+    // all streaming inputs of the point are requested before the first one is used (see dind_fast_unstructured_aos.cu)
     const uint32_t cell = P.cells ? __ldcs(P.cells + k) : 0u;
+    T xs[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) xs[d] = __ldcs(P.dim[d].t_eval + k);
+    const int64_t ko = P.perm ? (int64_t)__ldcs(P.perm + k) : k;   // cell-sorted plan: output position
 #pragma unroll
     for (int d = 0; d < N; ++d) {
         const DimParams<T>& D = P.dim[d];
-        const T x = __ldcs(D.t_eval + k);
+        const T x = xs[d];
         const int cached = P.cells ? cell_idx<T>(D, cell) : (P.use_cached_idx ? __ldcs(D.idx_eval + k) : 0);
         const int i0 = stencil_ct<T, W>(D, x, cached, w[d]);
         stride[d] = (int)D.u_stride;
@@ -77,7 +82,6 @@ __global__ void __launch_bounds__(UBLOCK) unstructured_kernel(const __grid_const
     }
     T den = T(1);
     if (NURBS) den = ContractU<T, N - 1, W>::run(P.wts + base, w, stride);
-    const int64_t ko = P.perm ? (int64_t)__ldcs(P.perm + k) : k;   // cell-sorted plan: scatter to the original position
     for (int c = 0; c < P.n_comp; ++c) {
         const T acc = ContractU<T, N - 1, W>::run(P.u + (int64_t)c * P.u_comp_stride + base, w, stride);
         __stcs(P.out + (int64_t)c * P.out_comp_stride + ko * P.out_point_stride, NURBS ? acc / den : acc);

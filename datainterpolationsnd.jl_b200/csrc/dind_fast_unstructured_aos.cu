@@ -67,7 +67,13 @@ __device__ __forceinline__ int stencil_ct(const DimParams<T>& D, T x, int cached
     return idx - W;
 }
 
-template <typename T, int N, int W, int C, bool WIDE, int MINB = 0>
+// COH: the points come in plan order (cell-sorted).  Then every streaming input of the point is requested before
+// the first one is used: the per-dimension stencils have control flow the compiler does not move loads across,
+// and one t_eval load per dimension in sequence is N dependent DRAM round trips (ncu source view, config 5 in plan
+// order: 34 % of all stall samples sat on them; 3.24 -> 2.54 ms).  With iid points the kernel is bound by the
+// DRAM sector traffic of the gather and the early loads cost 5 % (config 5: 33.0 -> 34.9 ms), so that
+// instantiation keeps the loads where they are used.
+template <typename T, int N, int W, int C, bool WIDE, bool COH, int MINB = 0>
 __global__ void __launch_bounds__(ABLOCK, MINB) unstructured_aos_kernel(const __grid_constant__ EvalParams<T> P) {
     const int64_t k = (int64_t)blockIdx.x * ABLOCK + threadIdx.x;
     if (k >= P.n_points) return;
@@ -76,16 +82,23 @@ __global__ void __launch_bounds__(ABLOCK, MINB) unstructured_aos_kernel(const __
     int stride[MAXN];
     int64_t base = 0;
     const uint32_t cell = P.cells ? __ldcs(P.cells + k) : 0u;
+    T xs[N];
+    int64_t ko = k;
+    if constexpr (COH) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) xs[d] = __ldcs(P.dim[d].t_eval + k);
+        if (P.perm) ko = (int64_t)__ldcs(P.perm + k);
+    }
 #pragma unroll
     for (int d = 0; d < N; ++d) {
         const DimParams<T>& D = P.dim[d];
-        const T x = __ldcs(D.t_eval + k);
+        const T x = COH ? xs[d] : __ldcs(D.t_eval + k);
         const int cached = P.cells ? cell_idx<T>(D, cell) : (P.use_cached_idx ? __ldcs(D.idx_eval + k) : 0);
         const int i0 = stencil_ct<T, W>(D, x, cached, w[d]);
         stride[d] = (int)D.u_stride * S;
         base += (int64_t)i0 * D.u_stride;
     }
-    const int64_t ko = P.perm ? (int64_t)__ldcs(P.perm + k) : k;
+    if constexpr (!COH) ko = P.perm ? (int64_t)__ldcs(P.perm + k) : k;
     const Vec<T, C> acc = ContractV<T, N - 1, W, C, WIDE>::run(P.u_aos + base * S, w, stride);
     if (P.staged_records) {   // cell-sorted plan: one aligned record per point
         store_record<T, C>(P.out + ko * P.out_point_stride, acc.v);
@@ -107,19 +120,22 @@ template <typename T, int N, int W>
 cudaError_t launch_aos(const EvalParams<T>& P, cudaStream_t s) {
     const unsigned nb = (unsigned)((P.n_points + ABLOCK - 1) / ABLOCK);
     const bool narrow = sizeof(T) == 8 && P.coherent_points;   // only 32-byte nodes have two load shapes
+    const bool coh = P.coherent_points != 0;
     switch (P.n_comp) {
-        case 2: unstructured_aos_kernel<T, N, W, 2, true><<<nb, ABLOCK, 0, s>>>(P); break;
+        case 2:
+            if (coh) unstructured_aos_kernel<T, N, W, 2, true, true><<<nb, ABLOCK, 0, s>>>(P);
+            else unstructured_aos_kernel<T, N, W, 2, true, false><<<nb, ABLOCK, 0, s>>>(P);
+            break;
         case 3:
             // config 3 in plan order: asking for 4 CTAs/SM (64 registers instead of the 60 ptxas picks on its own)
             // changes the schedule: 1.43 -> 1.33 ms; 3 CTAs (80 registers) 1.49, 5 (48) 1.36, 6 (40, spills) 1.58
-            if (narrow && W == 4 && N == 3) unstructured_aos_kernel<T, N, W, 3, sizeof(T) != 8, 4><<<nb, ABLOCK, 0, s>>>(P);
-            else
-            if (narrow) unstructured_aos_kernel<T, N, W, 3, sizeof(T) != 8><<<nb, ABLOCK, 0, s>>>(P);
-            else unstructured_aos_kernel<T, N, W, 3, true><<<nb, ABLOCK, 0, s>>>(P);
+            if (narrow && W == 4 && N == 3) unstructured_aos_kernel<T, N, W, 3, sizeof(T) != 8, true, 4><<<nb, ABLOCK, 0, s>>>(P);
+            else if (coh) unstructured_aos_kernel<T, N, W, 3, sizeof(T) != 8, true><<<nb, ABLOCK, 0, s>>>(P);
+            else unstructured_aos_kernel<T, N, W, 3, true, false><<<nb, ABLOCK, 0, s>>>(P);
             break;
         case 4:
-            if (narrow) unstructured_aos_kernel<T, N, W, 4, sizeof(T) != 8><<<nb, ABLOCK, 0, s>>>(P);
-            else unstructured_aos_kernel<T, N, W, 4, true><<<nb, ABLOCK, 0, s>>>(P);
+            if (coh) unstructured_aos_kernel<T, N, W, 4, sizeof(T) != 8, true><<<nb, ABLOCK, 0, s>>>(P);
+            else unstructured_aos_kernel<T, N, W, 4, true, false><<<nb, ABLOCK, 0, s>>>(P);
             break;
         default: return cudaErrorInvalidValue;
     }
