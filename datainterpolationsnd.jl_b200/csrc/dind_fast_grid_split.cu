@@ -265,7 +265,23 @@ __global__ void __launch_bounds__(S1_BLOCK) grid_slice_kernel(const __grid_const
         const T* srcw = (NARR == 2 ? Q.a1 : Q.premul) + sl * Q.slice_stride;
         if (NARR == 2 || Q.premul) {
             // NURBS numerator u*w (src/interpolation_methods.jl:124-131) formed here instead of by a separate pass
-            for (int i = threadIdx.x; i < nn; i += S1_BLOCK) {
+            // four elements per thread and step, all eight loads issued before the first shared-memory store
+            constexpr int U = 4;
+            int i = threadIdx.x;
+            for (; i + (U - 1) * S1_BLOCK < nn; i += U * S1_BLOCK) {
+                T uv[U], wv[U];
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    wv[q] = __ldg(srcw + i + q * S1_BLOCK);
+                    uv[q] = __ldcs(src0 + i + q * S1_BLOCK);
+                }
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    S[i + q * S1_BLOCK] = Q.premul ? uv[q] * wv[q] : uv[q];
+                    if (NARR == 2) S[nn + i + q * S1_BLOCK] = wv[q];
+                }
+            }
+            for (; i < nn; i += S1_BLOCK) {
                 const T wv = __ldg(srcw + i);
                 S[i] = Q.premul ? __ldcs(src0 + i) * wv : __ldcs(src0 + i);
                 if (NARR == 2) S[nn + i] = wv;
@@ -294,8 +310,24 @@ __global__ void __launch_bounds__(S1_BLOCK) grid_slice_kernel(const __grid_const
         const int g_lo = ch * S1_CHUNK, g_hi = min(Q.g2, g_lo + S1_CHUNK);
         T* o0 = Q.t0 + sl * out_slice + g1;
         T* o1 = NARR == 2 ? Q.t1 + sl * out_slice + g1 : nullptr;
+        // axis-2 table entry of the NEXT output is requested one step ahead: read where it is used, the
+        // L1 latency of i0_2[g] and w_2[g] sat in every step's dependent chain (ncu source view: 36 % of the
+        // kernel's stall samples)
+        int i2n = __ldg(Q.i0_2 + g_lo);
+        T w2n[W];
+#pragma unroll
+        for (int a = 0; a < W; ++a) w2n[a] = __ldg(Q.w_2 + g_lo * W + a);
         for (int g = g_lo; g < g_hi; ++g) {
-            const int i2 = __ldg(Q.i0_2 + g);
+            const int i2 = i2n;
+            T w2[W];
+#pragma unroll
+            for (int a = 0; a < W; ++a) w2[a] = w2n[a];
+            {
+                const int gn = min(g + 1, g_hi - 1);
+                i2n = __ldg(Q.i0_2 + gn);
+#pragma unroll
+                for (int a = 0; a < W; ++a) w2n[a] = __ldg(Q.w_2 + gn * W + a);
+            }
             if (i2 != cur) {
                 const int shift = (i2 > cur && i2 - cur < W) ? i2 - cur : W;
                 for (int s = 0; s < shift; ++s) {
@@ -316,7 +348,7 @@ __global__ void __launch_bounds__(S1_BLOCK) grid_slice_kernel(const __grid_const
             for (int k = 0; k < NARR; ++k) {
                 T acc = T(0);
 #pragma unroll
-                for (int a = 0; a < W; ++a) acc = fma(__ldg(Q.w_2 + g * W + a), win[k][a], acc);
+                for (int a = 0; a < W; ++a) acc = fma(w2[a], win[k][a], acc);
                 (k == 0 ? o0 : o1)[(int64_t)g * Q.g1] = acc;
             }
         }
