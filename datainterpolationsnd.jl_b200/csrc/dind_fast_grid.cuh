@@ -20,6 +20,7 @@
 // FP32/FP64 FMA pipes, not tensor cores (a per-axis band matrix is >98 % zeros).
 #pragma once
 #include <cmath>
+#include <initializer_list>
 #include <cstdlib>
 #include <cstring>
 
@@ -447,22 +448,32 @@ cudaError_t launch_pencil_cfg(const EvalParams<T>& P, cudaStream_t s) {
     // start-up), 86 -> 0.125, 128 -> 0.134 (too few CTAs: 1.4 waves)
     int chunk = 64;
     {
-        // ... unless 64 leaves a visibly emptier last wave than 32 (CTAs per SM as in the launch bounds), or there is
-        // no window to start up (W = 1): F64 trilinear 256^3 -> 512^3 3.46 waves vs 6.9: 636 vs 660 Gpoints/s
+        // ... unless 64 leaves a visibly emptier last wave than a shorter chunk (CTAs per SM as in the launch bounds):
+        // the longest of 64, 56, 48, 40, 32 that fills its last wave to >= 94 %, else the best-filled one.  Config 2
+        // (592 CTA slots): 64 -> 3.46 waves 0.114 ms, 48 -> 4.76 waves 0.108 ms, 32 -> 6.9 waves 0.111 ms.
+        // No window to start up (W = 1): 32.
         const bool pfk = !P.wts && sizeof(T) == 4 && W == 2;
         const double slots = 148.0 * ((pfk || sizeof(T) == 8 || W >= 3 || N >= 4) ? 4 : 8);
         auto fill = [&](int ch) {
             const double waves = (double)bx * ((n_last + ch - 1) / ch) / slots;
             return waves / ceil(waves);
         };
-        if (W == 1 || (fill(64) < 0.9 && fill(32) > fill(64) + 0.05)) chunk = 32;
+        if (W == 1) chunk = 32;
+        else {
+            double best = -1.0;
+            for (int ch : {64, 56, 48, 40, 32}) {
+                const double f = fill(ch);
+                if (f >= 0.94) { chunk = ch; break; }
+                if (f > best + 0.02) { best = f; chunk = ch; }
+            }
+        }
     }
     while (chunk > 8 && (int64_t)bx * ((n_last + chunk - 1) / chunk) < 148 * 5 * 2) chunk >>= 1;
     chunk = min(MAXCHUNK, max(1, env_int("DIND_CHUNK", chunk)));
     dim3 grid((unsigned)bx, (unsigned)((n_last + chunk - 1) / chunk));
     // L1 prefetch distance, measured: config 2 0 -> 0.133 ms, 1..3 -> 0.122 ms, 6 -> 0.128 ms; every W = 2 / 3 case
     // of scripts/sanity_perf.py gains 2-16 %, the W = 4 cases (long runs, 3-4x upsampling) lose 3-6 %
-    constexpr int pf1_default = W <= 3 ? 2 : 0;
+    constexpr int pf1_default = W <= 3 ? 4 : 0;   // 4 CTAs/SM: distance 4..8 beats 2 by 2 % on config 2 (L1 has the room)
     // warm L2 with u when it (plus the NURBS weights) fits comfortably and the pointers allow bulk prefetch; with the
     // L1 prefetch running ahead of the walk the warm-up only competes with it (config 2: 0.116 with, 0.114 ms without)
     const size_t u_bytes = (size_t)P.u_comp_stride * (P.n_comp + (P.wts ? 1 : 0)) * sizeof(T);
