@@ -33,7 +33,7 @@ METRIC = "Gpoints/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # `ncu --set full` captures (profiles/r1_<workload>.md); None where no capture exists.
-NCU_TRAFFIC = {"c2": 545_651_712, "c4": 3_386_374_000, "c1": 16_083_456, "c3": 1_015_403_008, "c5": 184_760_204_000}
+NCU_TRAFFIC = {"c2": 546_288_128, "c4": 3_386_374_000, "c1": 16_083_456, "c3": 1_015_403_008, "c5": 184_760_204_000}
 
 
 def measured_peaks():
