@@ -58,28 +58,33 @@ __device__ __forceinline__ int stencil_ct(const DimParams<T>& D, T x, int cached
     return idx - W;
 }
 
-template <typename T, int N, int W, bool NURBS>
+// COH: plan order — all streaming inputs of the point are requested before the first one is used; the iid
+// instantiation keeps each load at its use (see dind_fast_unstructured_aos.cu for the measurements)
+template <typename T, int N, int W, bool NURBS, bool COH>
 __global__ void __launch_bounds__(UBLOCK) unstructured_kernel(const __grid_constant__ EvalParams<T> P) {
     const int64_t k = (int64_t)blockIdx.x * UBLOCK + threadIdx.x;
     if (k >= P.n_points) return;
     T w[MAXN][W];
     int stride[MAXN];
     int64_t base = 0;
-    // all streaming inputs of the point are requested before the first one is used (see dind_fast_unstructured_aos.cu)
     const uint32_t cell = P.cells ? __ldcs(P.cells + k) : 0u;
     T xs[N];
+    int64_t ko = k;
+    if constexpr (COH) {
 #pragma unroll
-    for (int d = 0; d < N; ++d) xs[d] = __ldcs(P.dim[d].t_eval + k);
-    const int64_t ko = P.perm ? (int64_t)__ldcs(P.perm + k) : k;   // cell-sorted plan: output position
+        for (int d = 0; d < N; ++d) xs[d] = __ldcs(P.dim[d].t_eval + k);
+        if (P.perm) ko = (int64_t)__ldcs(P.perm + k);   // cell-sorted plan: output position
+    }
 #pragma unroll
     for (int d = 0; d < N; ++d) {
         const DimParams<T>& D = P.dim[d];
-        const T x = xs[d];
+        const T x = COH ? xs[d] : __ldcs(D.t_eval + k);
         const int cached = P.cells ? cell_idx<T>(D, cell) : (P.use_cached_idx ? __ldcs(D.idx_eval + k) : 0);
         const int i0 = stencil_ct<T, W>(D, x, cached, w[d]);
         stride[d] = (int)D.u_stride;
         base += (int64_t)i0 * D.u_stride;
     }
+    if constexpr (!COH) ko = P.perm ? (int64_t)__ldcs(P.perm + k) : k;
     T den = T(1);
     if (NURBS) den = ContractU<T, N - 1, W>::run(P.wts + base, w, stride);
     for (int c = 0; c < P.n_comp; ++c) {
@@ -91,8 +96,13 @@ __global__ void __launch_bounds__(UBLOCK) unstructured_kernel(const __grid_const
 template <typename T, int N, int W>
 cudaError_t launch_unstructured(const EvalParams<T>& P, cudaStream_t s) {
     const unsigned nb = (unsigned)((P.n_points + UBLOCK - 1) / UBLOCK);
-    if (P.wts) unstructured_kernel<T, N, W, true><<<nb, UBLOCK, 0, s>>>(P);
-    else unstructured_kernel<T, N, W, false><<<nb, UBLOCK, 0, s>>>(P);
+    if (P.coherent_points) {
+        if (P.wts) unstructured_kernel<T, N, W, true, true><<<nb, UBLOCK, 0, s>>>(P);
+        else unstructured_kernel<T, N, W, false, true><<<nb, UBLOCK, 0, s>>>(P);
+    } else {
+        if (P.wts) unstructured_kernel<T, N, W, true, false><<<nb, UBLOCK, 0, s>>>(P);
+        else unstructured_kernel<T, N, W, false, false><<<nb, UBLOCK, 0, s>>>(P);
+    }
     return cudaGetLastError();
 }
 
