@@ -9,6 +9,8 @@ SO_PATH = os.path.join(HERE, "libdind.so")
 
 OK = 0
 ERR_INVALID_ARGUMENT, ERR_SIZE_MISMATCH, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6
+ERR_NCCL = -7
+UNIQUE_ID_BYTES = 128
 F32, F64 = 0, 1
 LINEAR, CONSTANT, BSPLINE = 0, 1, 2
 FLAG_ASYNC, FLAG_COPY, FLAG_CACHED_IDX, FLAG_GENERIC, FLAG_CELL_SORTED = 1, 2, 4, 8, 16
@@ -39,6 +41,11 @@ SYMBOLS = [
     ("dind_last_kernel", C.c_char_p, [_vp]),
     ("dind_launch_count", _i64, [_vp]),
     ("dind_shard_range", _i, [_i64, _i, _i, _pi64, _pi64]),
+    ("dind_comm_get_unique_id", _i, [_vp]),
+    ("dind_comm_init", _i, [_vp, _vp, _i, _i]),
+    ("dind_comm_destroy", _i, [_vp]),
+    ("dind_comm_info", _i, [_vp, _pint, _pint, _pint]),
+    ("dind_allgather_out", _i, [_vp, _vp, _vp, _i64, _i64, _i64, _u]),
     ("dind_host_register", _i, [_vp, _i64]),
     ("dind_host_unregister", _i, [_vp]),
     ("dind_last_error", C.c_char_p, []),

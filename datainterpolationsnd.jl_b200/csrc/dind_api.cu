@@ -12,12 +12,11 @@
 #include <string>
 #include <vector>
 
-#include "../../include/dind.h"
-#include "dind_kernels.h"
+#include "dind_handle.h"
 
 using namespace dind;
 
-namespace {
+namespace dind {
 
 thread_local std::string g_last_error;
 
@@ -31,109 +30,9 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-#define CUDA_TRY(expr)                                                                                \
-    do {                                                                                              \
-        cudaError_t e_ = (expr);                                                                      \
-        if (e_ != cudaSuccess) {                                                                      \
-            cudaGetLastError();                                                                       \
-            return fail(DIND_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
-        }                                                                                             \
-    } while (0)
+void comm_release(dind_interp_s* h);   // dind_comm.cu
 
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    cudaError_t ensure(size_t bytes) {
-        if (bytes <= cap && p) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        if (bytes == 0) bytes = 16;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e == cudaSuccess) cap = bytes;
-        return e;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
-struct AxisTable {
-    int order = -1;
-    DevBuf i0, w, flag;
-};
-
-struct DimState {
-    bool set = false;
-    int kind = 0, degree = 0, left = 1;
-    std::vector<double> t;          // distinct knots (exact for both element types)
-    std::vector<int64_t> mult;
-    std::vector<double> knots;      // t, or knots_all for BSpline
-    int width = 0;
-    int64_t n_u = 0;                // expected size(u, dim)
-    DevBuf d_knots, d_keys, d_recip, d_lut;
-    int lut_n = 0;              // buckets of the search table (0 = none)
-    double lut_t0 = 0, lut_scale = 0;
-    // t_eval
-    bool teval_set = false;
-    const void* d_teval = nullptr;  // device pointer (owned copy or borrowed)
-    DevBuf teval_owned;
-    int64_t n_eval = 0;
-    int max_deriv = 0;
-    DevBuf d_idx;
-    bool idx_valid = false;
-    AxisTable table;
-    void invalidate_caches() {
-        idx_valid = false;
-        table.order = -1;
-    }
-    void release() {
-        d_knots.release(); d_keys.release(); d_recip.release(); d_lut.release(); teval_owned.release();
-        d_idx.release(); table.i0.release(); table.w.release(); table.flag.release();
-    }
-};
-
-}  // namespace
-
-struct dind_interp_s {
-    int n_in = 0, dtype = 0, device = 0;
-    size_t esz = 4;
-    cudaStream_t stream = nullptr;
-    DimState dims[MAXN];
-    // u
-    bool u_set = false;
-    const void* d_u = nullptr;
-    DevBuf u_owned;
-    std::vector<int64_t> u_dims;
-    int64_t comp_stride = 0, n_comp = 1;
-    // NURBS weights
-    bool w_set = false;
-    const void* d_w = nullptr;
-    DevBuf w_owned;
-    DevBuf uw;          // u pre-multiplied by the weights
-    bool uw_valid = false;
-    DevBuf split_scratch;   // stage-1 results of the two-stage 4-D grid evaluation
-    DevBuf u_aos;       // component-fastest copy of u (vector-valued unstructured evaluation)
-    bool u_aos_valid = false;
-    // cell-sorted plan for eval_unstructured (dind_plan.cu)
-    bool plan_valid = false;
-    int64_t plan_n = 0;
-    DevBuf plan_perm, plan_stage, plan_scratch, plan_slot2, plan_dest2, plan_cells;
-    bool plan_has_cells = false;   // plan_cells holds the packed cell words of the current plan
-    bool plan_buckets_valid = false;
-    DevBuf plan_t[MAXN];
-    // staging
-    DevBuf out_stage[2];            // host `out`: device staging, double buffered for the pipelined (ASYNC) path
-    int out_toggle = 0;
-    cudaStream_t copy_stream = nullptr;   // D2H of results, so that it overlaps the next step's H2D + kernel
-    cudaEvent_t ev_kernel = nullptr, ev_d2h[2] = {nullptr, nullptr};
-    DevBuf pts_stage[MAXN];
-    void* small_host = nullptr;     // pinned, device-mapped staging of the small-batch (latency) path of dind_eval_points
-    std::string last_kernel = "none";
-    int64_t launches = 0;
-};
+}  // namespace dind
 
 namespace {
 
@@ -145,15 +44,43 @@ constexpr unsigned DIND_FLAG_PUBLIC_MASK = ~(FLAG_OUT_MAPPED | FLAG_BUILD_ONLY);
 constexpr size_t SMALL_BYTES = 64 << 10;    // staging size of the small-batch path
 constexpr int64_t SMALL_POINTS = 2048;
 
-bool is_device_ptr(const void* p) {
+Knobs read_knobs() {
+    auto geti = [](const char* name, int dflt) {
+        const char* v = getenv(name);
+        return v ? atoi(v) : dflt;
+    };
+    Knobs k;
+    k.chunk = geti("DIND_CHUNK", 0);
+    k.pf = geti("DIND_PF", 1);
+    k.pf1 = geti("DIND_PF1", -1);
+    k.l2_warm = geti("DIND_L2_WARM", -1);
+    k.c3_tile = geti("DIND_C3_TILE", -1);
+    k.no_lut = getenv("DIND_NO_LUT") != nullptr;
+    k.no_split = getenv("DIND_NO_SPLIT") != nullptr;
+    k.no_cells = getenv("DIND_NO_CELLS") != nullptr;
+    k.no_aos = getenv("DIND_NO_AOS") != nullptr;
+    k.no_small = getenv("DIND_NO_SMALL") != nullptr;
+    k.no_slice = getenv("DIND_NO_SLICE") != nullptr;
+    k.no_persist = getenv("DIND_NO_PERSIST") != nullptr;
+    return k;
+}
+
+// dev_out (optional): the ordinal of the device that owns a cudaMalloc'ed pointer, -1 for host / managed memory
+bool is_device_ptr(const void* p, int* dev_out = nullptr) {
     cudaPointerAttributes a;
+    if (dev_out) *dev_out = -1;
     cudaError_t e = cudaPointerGetAttributes(&a, p);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
+    if (a.type == cudaMemoryTypeDevice && dev_out) *dev_out = a.device;
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
+
+// A device pointer handed to a handle must live on the handle's device (the kernels dereference it there).
+int check_ptr_device(const dind_interp_s* h, const void* p, const char* what);
+
 
 template <typename T>
 int upload_dim(dind_interp_s* h, DimState& D) {
@@ -189,7 +116,7 @@ int upload_dim(dind_interp_s* h, DimState& D) {
     // bucket table for the interval search: ~4 buckets per knot, built on the device with the
     // same arithmetic the kernels use (dind_device.cuh: lut_bucket)
     D.lut_n = 0;
-    if (n >= 8 && !getenv("DIND_NO_LUT")) {
+    if (n >= 8 && !h->knobs.no_lut) {
         int nb = 32;
         while (nb < 4 * n && nb < 4096) nb <<= 1;
         const T t0 = kn[0];
@@ -243,6 +170,13 @@ int check_handle(dind_handle_t h) {
     return DIND_OK;
 }
 
+int check_ptr_device(const dind_interp_s* h, const void* p, const char* what) {
+    int dev = -1;
+    if (p && is_device_ptr(p, &dev) && dev >= 0 && dev != h->device)
+        return fail(DIND_ERR_INVALID_ARGUMENT, "%s is memory of device %d, the handle lives on device %d", what, dev, h->device);
+    return DIND_OK;
+}
+
 int check_dim(dind_handle_t h, int dim) {
     if (dim < 0 || dim >= h->n_in) return fail(DIND_ERR_INVALID_ARGUMENT, "dimension %d out of range 0..%d", dim, h->n_in - 1);
     return DIND_OK;
@@ -289,6 +223,10 @@ int validate_interp(dind_interp_s* h) {
     // NURBS weights with Constant dimensions mixed in are an extension (no reference semantics: the
     // weights multiply the tensor-product stencil weights); Linear dimensions are rejected — the
     // reference would log an @error and silently ignore the weights (interpolation_utils.jl:65-67).
+    if (h->w_set)   // validate_cache (src/interpolation_utils.jl:56-63): size(weights) == size(u)[1:N_in], whatever the call order was
+        for (int d = 0; d < h->n_in; ++d)
+            if ((int)h->w_dims.size() != h->n_in || h->w_dims[d] != h->u_dims[d])
+                return fail(DIND_ERR_SIZE_MISMATCH, "The size of the weights array must match the length of the first N_in dimensions of u.");
     if (h->w_set)
         for (int d = 0; d < h->n_in; ++d)
             if (h->dims[d].kind == LINEAR)
@@ -339,6 +277,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     int rc = DIND_OK;
     EvalParams<T> P;
     memset(&P, 0, sizeof P);
+    P.knobs = &h->knobs;
     bool const_deriv = false, zero_result = false;
     for (int d = 0; d < N; ++d) {
         DimState& D = h->dims[d];
@@ -384,7 +323,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     P.n_comp = (int32_t)h->n_comp;
     // NURBS numerator u*w: a separate pass per dind_set_u, except where the kernel forms it while staging u
     bool split = grid && !(flags & DIND_FLAG_GENERIC) && !const_deriv && !zero_result && grid_split_supported<T>(P) &&
-                 !getenv("DIND_NO_SPLIT");
+                 !h->knobs.no_split;
     if (split && h->split_scratch.ensure(grid_split_scratch_bytes<T>(P)) != cudaSuccess) {
         cudaGetLastError();   // no room for the stage-1 results (at most 2x the size of out): one-pass kernel instead
         split = false;
@@ -419,7 +358,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         // (Linear / BSpline dimensions; a Constant dimension's node is not its interval index)
         int cell_bits = 0;
         for (int d = 0; d < N && cell_bits >= 0; ++d) {
-            if (P.dim[d].kind == CONSTANT || getenv("DIND_NO_CELLS")) { cell_bits = -1; break; }
+            if (P.dim[d].kind == CONSTANT || h->knobs.no_cells) { cell_bits = -1; break; }
             int b = 1;
             while ((1 << b) < P.dim[d].n_u) ++b;
             P.dim[d].cell_shift = cell_bits;
@@ -494,7 +433,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
 
     const bool fast_ok = !(flags & DIND_FLAG_GENERIC) && !const_deriv && !zero_result;
     // vector-valued u: gather from the component-fastest copy (rebuilt once per dind_set_u)
-    const bool use_aos = fast_ok && !grid && aos_supported<T>(P) && !getenv("DIND_NO_AOS");
+    const bool use_aos = fast_ok && !grid && aos_supported<T>(P) && !h->knobs.no_aos;
     if (use_aos) {
         if (!h->u_aos_valid) {
             CUDA_TRY(h->u_aos.ensure((size_t)h->comp_stride * aos_node_stride((int)h->n_comp) * sizeof(T)));
@@ -587,6 +526,7 @@ int eval_cached(dind_interp_s* h, void* out, const int* orders_in, bool grid, un
             if (n_eval[d] != n_eval[0])
                 return fail(DIND_ERR_SIZE_MISMATCH, "The t_eval of all interpolation dimensions must have the same length as the first dimension of out.");
     if (!out && !(flags & FLAG_BUILD_ONLY)) return fail(DIND_ERR_INVALID_ARGUMENT, "out is NULL");
+    if ((rc = check_ptr_device(h, out, "out"))) return rc;
     return run_eval<T>(h, out, orders, grid, t_dev, n_eval, true, flags);
 }
 
@@ -601,13 +541,15 @@ int eval_points(dind_interp_s* h, void* out, const void* const* t, int64_t n, co
     if (!out || !t) return fail(DIND_ERR_INVALID_ARGUMENT, "out / t is NULL");
     const void* t_dev[MAXN];
     int64_t n_eval[MAXN];
+    if ((rc = check_ptr_device(h, out, "out"))) return rc;
     bool all_host = !is_device_ptr(out);
     for (int d = 0; d < h->n_in; ++d) {
         if (!t[d]) return fail(DIND_ERR_INVALID_ARGUMENT, "t[%d] is NULL", d);
+        if ((rc = check_ptr_device(h, t[d], "t"))) return rc;
         n_eval[d] = n;
         all_host = all_host && !is_device_ptr(t[d]);
     }
-    flags &= ~(DIND_FLAG_CACHED_IDX | FLAG_OUT_MAPPED);
+    flags &= DIND_FLAG_PUBLIC_MASK & ~DIND_FLAG_CACHED_IDX;
     // Small-batch (latency) path — the single-point callable interp(t...) and ODE right-hand sides
     // (SURVEY.md §8f-4): the coordinates and the results travel through one pinned, device-mapped
     // staging buffer, so a call is ONE kernel launch + one stream synchronisation and no copy call.
@@ -615,7 +557,7 @@ int eval_points(dind_interp_s* h, void* out, const void* const* t, int64_t n, co
     const size_t t_slot = (t_bytes + 15) & ~size_t(15);
     const size_t out_bytes = (size_t)n * h->n_comp * sizeof(T);
     if (all_host && n > 0 && n <= SMALL_POINTS && !(flags & DIND_FLAG_ASYNC) && t_slot * h->n_in + out_bytes <= SMALL_BYTES &&
-        !getenv("DIND_NO_SMALL")) {   // experiment knob: force the copy path
+        !h->knobs.no_small) {   // experiment knob: force the copy path
         if (!h->small_host) CUDA_TRY(cudaHostAlloc(&h->small_host, SMALL_BYTES, cudaHostAllocMapped));
         char* base = (char*)h->small_host;
         for (int d = 0; d < h->n_in; ++d) {
@@ -678,6 +620,7 @@ int dind_create(dind_handle_t* handle, int n_in, int dtype, int device) {
     h->dtype = dtype;
     h->device = device;
     h->esz = dtype == DIND_F32 ? 4 : 8;
+    h->knobs = read_knobs();
     *handle = h;
     return DIND_OK;
 }
@@ -695,6 +638,7 @@ int dind_destroy(dind_handle_t h) {
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_kernel) cudaEventDestroy(h->ev_kernel);
     for (int i = 0; i < 2; ++i) if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
+    comm_release(h);
     h->plan_perm.release(); h->plan_stage.release(); h->plan_scratch.release(); h->plan_slot2.release(); h->plan_dest2.release(); h->plan_cells.release();
     for (int d = 0; d < MAXN; ++d) h->plan_t[d].release();
     delete h;
@@ -728,6 +672,7 @@ int dind_set_dim(dind_handle_t h, int dim, int kind, const void* t, int64_t n_t,
     std::vector<double> tv((size_t)n_t);
     std::vector<char> tmp;
     const void* src = t;
+    if ((rc = check_ptr_device(h, t, "t"))) return rc;
     if (is_device_ptr(t)) {
         tmp.resize((size_t)n_t * h->esz);
         CUDA_TRY(cudaMemcpy(tmp.data(), t, tmp.size(), cudaMemcpyDeviceToHost));
@@ -739,47 +684,52 @@ int dind_set_dim(dind_handle_t h, int dim, int kind, const void* t, int64_t n_t,
         if (!(tv[i] - tv[i - 1] > 0)) return fail(DIND_ERR_INVALID_ARGUMENT, "The elements of t must be sorted and unique.");
     if (std::isnan(tv[0])) return fail(DIND_ERR_INVALID_ARGUMENT, "The elements of t must be sorted and unique.");
 
-    DimState& D = h->dims[dim];
-    D.kind = kind;
-    D.left = left;
-    D.degree = 0;
-    D.t = tv;
-    D.mult.clear();
+    // Validate and derive everything in locals; the dimension's state is replaced only when all of it succeeded,
+    // so a failing call leaves the previous (consistent) dimension in place.
+    int n_degree = 0, n_width = 0;
+    int64_t n_nu = 0;
+    std::vector<int64_t> mult;
+    std::vector<double> knots;
     if (kind == DIND_BSPLINE) {
         if (degree < 0) return fail(DIND_ERR_INVALID_ARGUMENT, "degree must be non-negative");
         if (degree > DIND_MAX_DEGREE) return fail(DIND_ERR_UNSUPPORTED, "B-spline degree %d > %d is not supported", degree, DIND_MAX_DEGREE);
-        D.degree = degree;
-        if (multiplicities) D.mult.assign(multiplicities, multiplicities + n_t);
+        n_degree = degree;
+        if (multiplicities) mult.assign(multiplicities, multiplicities + n_t);
         else {   // open/clamped knot vector (src/interpolation_dimensions.jl:168-173)
-            D.mult.assign((size_t)n_t, 1);
-            D.mult[0] = degree + 1;
-            D.mult[(size_t)n_t - 1] = degree + 1;
+            mult.assign((size_t)n_t, 1);
+            mult[0] = degree + 1;
+            mult[(size_t)n_t - 1] = degree + 1;
         }
         for (int64_t i = 0; i < n_t; ++i)   // :175
-            if (D.mult[i] < 1 || D.mult[i] > degree + 1) {
-                D.set = false;
+            if (mult[i] < 1 || mult[i] > degree + 1)
                 return fail(DIND_ERR_INVALID_ARGUMENT, "All multiplicities must be between 1 and degree + 1.");
-            }
-        D.knots.clear();
         for (int64_t i = 0; i < n_t; ++i)   // expand_knot_vector_kernel (src/spline_utils.jl:1-20)
-            for (int64_t m = 0; m < D.mult[i]; ++m) D.knots.push_back(tv[i]);
-        D.width = degree + 1;
-        D.n_u = (int64_t)D.knots.size() - degree - 1;   // get_n_basis_functions (:223-225)
-        if (D.n_u < degree + 1) {
-            D.set = false;
-            return fail(DIND_ERR_INVALID_ARGUMENT, "knot vector too short for degree %d (%lld basis functions)", degree, (long long)D.n_u);
-        }
+            for (int64_t m = 0; m < mult[i]; ++m) knots.push_back(tv[i]);
+        n_width = degree + 1;
+        n_nu = (int64_t)knots.size() - degree - 1;   // get_n_basis_functions (:223-225)
+        if (n_nu < degree + 1)
+            return fail(DIND_ERR_INVALID_ARGUMENT, "knot vector too short for degree %d (%lld basis functions)", degree, (long long)n_nu);
     } else {
         if (n_t < 2) return fail(DIND_ERR_INVALID_ARGUMENT, "Linear/Constant dimensions need at least 2 knots");
-        D.knots = tv;
-        D.width = kind == DIND_LINEAR ? 2 : 1;
-        D.n_u = n_t;
+        knots = tv;
+        n_width = kind == DIND_LINEAR ? 2 : 1;
+        n_nu = n_t;
     }
+    DimState& D = h->dims[dim];
+    D.set = false;   // from here on the device tables are being rewritten: a CUDA failure leaves the dimension unset
+    D.invalidate_caches();
+    h->plan_valid = false;
+    D.kind = kind;
+    D.left = left;
+    D.degree = n_degree;
+    D.t = tv;
+    D.mult = mult;
+    D.knots = knots;
+    D.width = n_width;
+    D.n_u = n_nu;
     rc = h->dtype == DIND_F32 ? upload_dim<float>(h, D) : upload_dim<double>(h, D);
     if (rc) return rc;
     D.set = true;
-    D.invalidate_caches();
-    h->plan_valid = false;
     return DIND_OK;
 }
 
@@ -791,6 +741,7 @@ int dind_set_t_eval(dind_handle_t h, int dim, const void* t_eval, int64_t n_eval
     if (n_eval < 0) return fail(DIND_ERR_INVALID_ARGUMENT, "n_eval must be non-negative");
     if (n_eval > 0 && !t_eval) return fail(DIND_ERR_INVALID_ARGUMENT, "t_eval is NULL");
     if (max_derivative_order_eval < 0) return fail(DIND_ERR_INVALID_ARGUMENT, "max_derivative_order_eval must be non-negative");
+    if ((rc = check_ptr_device(h, t_eval, "t_eval"))) return rc;
     DimState& D = h->dims[dim];
     const size_t bytes = (size_t)n_eval * h->esz;
     if (n_eval > 0 && is_device_ptr(t_eval) && !(flags & DIND_FLAG_COPY)) {
@@ -827,12 +778,11 @@ int dind_set_u(dind_handle_t h, const void* u, const int64_t* dims, int ndims, u
         if (h->dims[d].set && dims[d] != h->dims[d].n_u)
             return fail(DIND_ERR_SIZE_MISMATCH, "size(u, %d) is %lld, the interpolation dimension expects %lld.", d + 1,
                         (long long)dims[d], (long long)h->dims[d].n_u);
-    if (h->w_set) {
-        int64_t wn = 1;
-        for (int d = 0; d < h->n_in; ++d) wn *= dims[d];
-        if (wn != h->comp_stride && h->u_set)
-            return fail(DIND_ERR_SIZE_MISMATCH, "size(u)[1:N_in] changed while NURBS weights are set; reset the weights first");
-    }
+    if (h->w_set)
+        for (int d = 0; d < h->n_in; ++d)
+            if ((int)h->w_dims.size() != h->n_in || h->w_dims[d] != dims[d])   // validate_cache (src/interpolation_utils.jl:56-63)
+                return fail(DIND_ERR_SIZE_MISMATCH, "The size of the weights array must match the length of the first N_in dimensions of u.");
+    if ((rc = check_ptr_device(h, u, "u"))) return rc;
     const size_t bytes = (size_t)comp_stride * n_comp * h->esz;
     if (is_device_ptr(u) && !(flags & DIND_FLAG_COPY)) {
         h->d_u = u;   // borrowed
@@ -861,8 +811,10 @@ int dind_set_weights(dind_handle_t h, const void* weights, const int64_t* dims, 
     if (!weights) {
         h->w_set = false;
         h->d_w = nullptr;
+        h->w_dims.clear();
         return DIND_OK;
     }
+    if ((rc = check_ptr_device(h, weights, "weights"))) return rc;
     if (!dims || ndims != h->n_in)
         return fail(DIND_ERR_SIZE_MISMATCH, "The size of the weights array must match the length of the first N_in dimensions of u.");
     int64_t n = 1;
@@ -883,6 +835,7 @@ int dind_set_weights(dind_handle_t h, const void* weights, const int64_t* dims, 
         if (!is_device_ptr(weights)) CUDA_TRY(cudaStreamSynchronize(h->stream));
         h->d_w = h->w_owned.p;
     }
+    h->w_dims.assign(dims, dims + ndims);
     h->w_set = true;
     return DIND_OK;
 }
@@ -925,6 +878,7 @@ int eval_gradient(dind_interp_s* h, void* out, unsigned flags) {
             return fail(DIND_ERR_SIZE_MISMATCH, "The t_eval of all interpolation dimensions must have the same length as the first dimension of out.");
     }
     if (!out) return fail(DIND_ERR_INVALID_ARGUMENT, "out is NULL");
+    if ((rc = check_ptr_device(h, out, "out"))) return rc;
     return run_eval<T>(h, out, orders, false, t_dev, n_eval, true, flags & ~DIND_FLAG_CACHED_IDX, true);
 }
 }  // namespace

@@ -137,8 +137,21 @@ struct DimParams {
     int32_t cell_shift, cell_mask, cell_add;
 };
 
+// Experiment knobs (DIND_* environment variables; not part of the API).  Read from the environment ONCE per
+// handle, in dind_create, and carried to the launchers by pointer: the evaluation path never calls getenv.
+struct Knobs {
+    int chunk = 0;       // DIND_CHUNK: pencil chunk length (0 = chosen by the launcher)
+    int pf = 1;          // DIND_PF: one-run-ahead register prefetch of the pencil kernel
+    int pf1 = -1;        // DIND_PF1: L1 prefetch distance (-1 = default of the instantiation)
+    int l2_warm = -1;    // DIND_L2_WARM: bulk L2 warm-up of u (-1 = default)
+    int c3_tile = -1;    // DIND_C3_TILE: points per thread of the cell-sorted cubic kernel (-1 = default)
+    bool no_lut = false, no_split = false, no_cells = false, no_aos = false, no_small = false, no_slice = false;
+    bool no_persist = false;   // DIND_NO_PERSIST: two launches instead of the persistent two-stage grid kernel
+};
+
 template <typename T>
 struct EvalParams {
+    const Knobs* knobs;    // host pointer (never dereferenced on the device); null = defaults
     DimParams<T> dim[MAXN];
     const T* u;            // (n_1..n_N, comps): NURBS: pre-multiplied by the weights
     const T* wts;          // NURBS weights (n_1..n_N) or null

@@ -34,10 +34,9 @@ constexpr int PBLOCK = 128;
 constexpr int PWARPS = PBLOCK / 32;
 constexpr int MAXCHUNK = 128;
 
-// tuning knob for experiments (not part of the API): DIND_CHUNK=<1..64>
-inline int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
+inline const Knobs& knobs_of(const Knobs* k) {
+    static const Knobs defaults;
+    return k ? *k : defaults;
 }
 
 // Bulk L2 prefetch through the TMA unit (SASS: UBLKPF.L2); addr and bytes are multiples of 16.
@@ -469,7 +468,9 @@ cudaError_t launch_pencil_cfg(const EvalParams<T>& P, cudaStream_t s) {
         }
     }
     while (chunk > 8 && (int64_t)bx * ((n_last + chunk - 1) / chunk) < 148 * 5 * 2) chunk >>= 1;
-    chunk = min(MAXCHUNK, max(1, env_int("DIND_CHUNK", chunk)));
+    const Knobs& K = knobs_of(P.knobs);
+    if (K.chunk > 0) chunk = K.chunk;
+    chunk = min(MAXCHUNK, max(1, chunk));
     dim3 grid((unsigned)bx, (unsigned)((n_last + chunk - 1) / chunk));
     // L1 prefetch distance, measured: config 2 0 -> 0.133 ms, 1..3 -> 0.122 ms, 6 -> 0.128 ms; every W = 2 / 3 case
     // of scripts/sanity_perf.py gains 2-16 %, the W = 4 cases (long runs, 3-4x upsampling) lose 3-6 %
@@ -479,10 +480,10 @@ cudaError_t launch_pencil_cfg(const EvalParams<T>& P, cudaStream_t s) {
     const size_t u_bytes = (size_t)P.u_comp_stride * (P.n_comp + (P.wts ? 1 : 0)) * sizeof(T);
     int l2_warm = u_bytes >= (1u << 20) && u_bytes <= (96u << 20) && reinterpret_cast<uintptr_t>(P.u) % 16 == 0 &&
                   (!P.wts || reinterpret_cast<uintptr_t>(P.wts) % 16 == 0);
-    l2_warm = env_int("DIND_L2_WARM", l2_warm && pf1_default == 0);
+    l2_warm = K.l2_warm >= 0 ? K.l2_warm : (l2_warm && pf1_default == 0);
     const bool full = n1 % (32 * VX) == 0 && (N < 3 || P.dim[1].n_eval % J == 0);
-    const bool pf = env_int("DIND_PF", 1) != 0;
-    const int pf1 = env_int("DIND_PF1", pf1_default);
+    const bool pf = K.pf != 0;
+    const int pf1 = K.pf1 >= 0 ? K.pf1 : pf1_default;
     if (P.wts) {
         if (full) grid_pencil_kernel<T, N, W, VX, J, true, true, false><<<grid, PBLOCK, 0, s>>>(P, (int)items, nseg, n2g, chunk, l2_warm, pf1);
         else grid_pencil_kernel<T, N, W, VX, J, true, false, false><<<grid, PBLOCK, 0, s>>>(P, (int)items, nseg, n2g, chunk, l2_warm, pf1);

@@ -412,7 +412,7 @@ bool grid_split_slice_ok(const EvalParams<T>& P) {
     const int64_t n1 = P.dim[0].n_u, n2 = P.dim[1].n_u, n3 = P.dim[2].n_u;
     const size_t slice_bytes = (size_t)n1 * n2 * sizeof(T) * (P.wts ? 2 : 1);
     return slice_bytes <= 96 * 1024 && P.dim[0].u_stride == 1 && P.dim[1].u_stride == n1 && P.dim[2].u_stride == n1 * n2 &&
-           P.dim[3].u_stride == n1 * n2 * n3 && P.dim[0].n_eval < (1 << 24) && !getenv("DIND_NO_SLICE");
+           P.dim[3].u_stride == n1 * n2 * n3 && P.dim[0].n_eval < (1 << 24) && !(P.knobs && P.knobs->no_slice);
 }
 
 template <typename T>

@@ -49,6 +49,7 @@ extern "C" {
 #define DIND_ERR_CUDA (-4)             /* CUDA runtime error, message has the CUDA error string  */
 #define DIND_ERR_STATE (-5)            /* call order: e.g. eval before set_u / set_t_eval        */
 #define DIND_ERR_NO_DEVICE (-6)        /* no usable CUDA device: there is no CPU fallback        */
+#define DIND_ERR_NCCL (-7)             /* NCCL missing (libnccl.so.2 is bound at run time) or an NCCL call failed */
 
 /* element types (eltype(u); knots, t_eval and out use the same type) */
 #define DIND_F32 0
@@ -100,7 +101,8 @@ int dind_synchronize(dind_handle_t handle);
  * :87-94, :162-204 — including validate_t (src/interpolation_utils.jl:34-37), the default
  * clamped multiplicities (:168-173), the multiplicity asserts (:174-175) and the knot
  * expansion kernel (src/spline_utils.jl:1-20).
- * `t`: n_t strictly increasing knots (host pointer). `degree`, `multiplicities` (host, n_t
+ * `t`: n_t strictly increasing knots (host or device pointer; always copied).  A failing call leaves the
+ * dimension as it was. `degree`, `multiplicities` (host, n_t
  * entries or NULL = clamped) only for DIND_BSPLINE. `left` is stored and, exactly like the
  * reference's field (src/interpolation_dimensions.jl:67), never read by evaluation. */
 int dind_set_dim(dind_handle_t handle, int dim, int kind, const void* t, int64_t n_t, int degree,
@@ -186,6 +188,34 @@ int64_t dind_launch_count(dind_handle_t handle);
  * interpolation axis (grids); each rank creates its own handle over its slice of t_eval.
  * [lo, hi) = the part of 0..n-1 owned by `rank` of `world`; ranges differ by at most 1. */
 int dind_shard_range(int64_t n, int rank, int world, int64_t* lo, int64_t* hi);
+
+/* Optional all-gather of the outputs of a sharded evaluation (north star (5); the reference has no multi-device
+ * path — src/interpolation_parallel.jl:34-52, :85-103 evaluate on ONE backend).  One process per GPU; the handle
+ * owns the NCCL communicator.  NCCL (libnccl.so.2) is bound at run time by the first of these calls, so a
+ * single-GPU host needs no NCCL; DIND_ERR_NCCL if it cannot be loaded.
+ *   dind_comm_get_unique_id: rank 0 creates the 128-byte id and hands it to the other ranks by any means (MPI.jl
+ *     bcast, a file, torch.distributed, ...);
+ *   dind_comm_init: collective over the `world` handles, each on its own device; replaces a previous communicator;
+ *   dind_comm_destroy: also done by dind_destroy. */
+#define DIND_UNIQUE_ID_BYTES 128
+int dind_comm_get_unique_id(void* id_out /* host, DIND_UNIQUE_ID_BYTES */);
+int dind_comm_init(dind_handle_t handle, const void* unique_id, int rank, int world);
+int dind_comm_destroy(dind_handle_t handle);
+/* rank / world of the handle's communicator (0 / 1 without one) and the version of the bound NCCL; any may be NULL */
+int dind_comm_info(dind_handle_t handle, int* rank, int* world, int* nccl_version);
+/* Collective.  Every rank passes its local output and receives the global one, both DEVICE arrays of the handle's
+ * element type, column-major:
+ *     out_local  (unit, n_local, n_comp)      n_local = hi - lo of dind_shard_range(n_total, rank, world)
+ *     out_global (unit, n_total, n_comp)
+ * eval_unstructured shards: unit = 1, n_total = global number of points, n_comp = prod(out dims)
+ *     (x (n_in + 1) for dind_eval_unstructured_gradient);
+ * eval_grid slabs: unit = g_1 * .. * g_{N-1}, n_total = global length of the last grid axis.
+ * Every component column travels straight from out_local into its final place in out_global (one ncclAllGather per
+ * column inside ncclGroupStart/End; ncclBroadcast per rank and column when n_total % world != 0): no staging, no
+ * padding, no re-packing.  Runs on the handle's stream after whatever was queued there (DIND_FLAG_ASYNC: returns
+ * without waiting).  Without a communicator (world = 1) it is a device copy (or nothing when the pointers are equal). */
+int dind_allgather_out(dind_handle_t handle, const void* out_local, void* out_global, int64_t n_total, int64_t unit,
+                       int64_t n_comp, unsigned flags);
 
 /* ---- pinned host memory (for the host-buffer path) ---------------------------------------- */
 int dind_host_register(void* ptr, int64_t bytes);

@@ -11,7 +11,22 @@ from oracle import oracle as O
 TOL = {np.dtype(np.float64): 1e-12, np.dtype(np.float32): 1e-5}
 
 
+# observed error / tolerance of every assert_close call, keyed by the running test: tests/conftest.py writes
+# the per-test maximum to gpurun_out/parity_observed.json (and profiles/ keeps a copy of the last GPU run)
+OBSERVED = {}
+
+
+def record_observed(ratio, rel):
+    import os
+    test = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+    prev = OBSERVED.get(test, (0.0, 0.0))
+    OBSERVED[test] = (max(prev[0], float(ratio)), max(prev[1], float(rel)))
+
+
 def assert_close(got, ref, dtype, factor=1.0):
+    """|got - ref| <= factor * TOL * max|ref|.  `factor` stays 1 (the north-star tolerance) unless the call site
+    gives a one-line reason; DIND_TOL_SOFT=1 records the observed ratio without failing (survey runs)."""
+    import os
     got, ref = np.asarray(got), np.asarray(ref)
     assert got.shape == ref.shape, (got.shape, ref.shape)
     nan_g, nan_r = np.isnan(got), np.isnan(ref)
@@ -19,6 +34,9 @@ def assert_close(got, ref, dtype, factor=1.0):
     scale = np.max(np.abs(ref[~nan_r])) if np.any(~nan_r) else 1.0
     scale = max(scale, np.finfo(dtype).tiny)
     err = np.max(np.abs(got[~nan_r] - ref[~nan_r])) if np.any(~nan_r) else 0.0
+    record_observed(err / (TOL[np.dtype(dtype)] * scale), err / scale)
+    if os.environ.get("DIND_TOL_SOFT"):
+        return
     assert err <= factor * TOL[np.dtype(dtype)] * scale, f"max err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.3e})"
 
 
@@ -88,3 +106,50 @@ def zipped_queries(rng, ts, n, dtype, outside=True):
     xs = [query(rng, t, n, dtype, outside=outside) for t in ts]
     m = min(x.size for x in xs)
     return [x[:m] for x in xs]
+
+
+# ---- counter-based RNG keyed by (seed, dim, GLOBAL point index) ------------------------------------------------
+# anything >= 1e8 points is generated on the device, per shard, from the global index, so that any
+# rank (or a single GPU, or the CPU oracle on a subsample) regenerates exactly the same point.  A 32-bit integer
+# hash evaluated in int64 with the value masked to 32 bits after every step: numpy and torch give identical bits.
+def counter_u01(idx, dim, seed):
+    """idx: int64 numpy array or torch tensor of global indices -> float64 uniforms in [0, 1)."""
+    M = 0xFFFFFFFF
+    x = (idx & M) ^ (((idx >> 32) * 0x9E3779B1) & M)
+    x = (x + ((dim * 0x85EBCA6B + seed * 0xC2B2AE35 + 0x27D4EB2F) & M)) & M
+    x = x ^ (x >> 16)
+    x = (x * 0x7FEB352D) & M
+    x = x ^ (x >> 15)
+    x = (x * 0x846CA68B) & M
+    x = x ^ (x >> 16)
+    if hasattr(x, "numpy") or type(x).__module__.startswith("torch"):
+        import torch
+        return x.to(torch.float64) * (1.0 / 4294967296.0)
+    return x.astype(np.float64) * (1.0 / 4294967296.0)
+
+
+def counter_points_np(idx, ts, seed, dtype, overshoot=0.0):
+    """Per-dimension coordinates of the global points `idx` (numpy int64): uniform over the knot span, stretched by
+    `overshoot` of the span on both sides (so a fraction of the points extrapolates)."""
+    idx = np.asarray(idx, dtype=np.int64)
+    out = []
+    for d, t in enumerate(ts):
+        t0, t1 = float(t[0]), float(t[-1])
+        a, b = t0 - overshoot * (t1 - t0), (t1 - t0) * (1.0 + 2.0 * overshoot)
+        out.append((a + counter_u01(idx, d, seed) * b).astype(dtype))
+    return out
+
+
+def counter_points_torch(lo, hi, ts, seed, dtype, device, overshoot=0.0, chunk=1 << 26):
+    """The same points for the contiguous global range [lo, hi), generated on `device` in chunks."""
+    import torch
+    tdt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+    outs = [torch.empty(hi - lo, dtype=tdt, device=device) for _ in ts]
+    for c0 in range(lo, hi, chunk):
+        c1 = min(hi, c0 + chunk)
+        idx = torch.arange(c0, c1, dtype=torch.int64, device=device)
+        for d, t in enumerate(ts):
+            t0, t1 = float(t[0]), float(t[-1])
+            a, b = t0 - overshoot * (t1 - t0), (t1 - t0) * (1.0 + 2.0 * overshoot)
+            outs[d][c0 - lo:c1 - lo] = (a + counter_u01(idx, d, seed) * b).to(tdt)
+    return outs

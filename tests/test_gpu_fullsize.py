@@ -116,37 +116,63 @@ def test_c1_full_size_against_oracle(D, torch):
     itp.close()
 
 
-# ---- config 3: 3-D cubic BSpline, u (128,128,128,3) Float64 ----------------------------------------------
-def test_c3_properties_and_subsample(D, torch):
+# ---- config 3: 3-D cubic BSpline, u (128,128,128,3) Float64, 10^8 zipped points + first derivatives --------
+def test_c3_full_size_1e8_points(D, torch):
+    """BASELINE configs[2] at its named size: 10^8 points, value and the three first partials.  Points come from the
+    counter-based generator (tests/helpers.py) so the oracle regenerates any subsample; 1 % of the span on either
+    side extrapolates."""
+    from tests import helpers as H
     rng = np.random.default_rng(3)
     ts = [knots(rng, 126, np.float64) for _ in range(3)]
-    n = 20_000_000
-    gen = torch.Generator(device="cuda").manual_seed(7)
-    xs_d = [torch.rand(n, generator=gen, device="cuda", dtype=torch.float64) * float(t[-1] - t[0]) + float(t[0]) for t in ts]
+    n = 100_000_000
+    xs_d = H.counter_points_torch(0, n, ts, 31, np.float64, "cuda", overshoot=0.01)
     dims = tuple(D.BSplineInterpolationDimension(t, 3, t_eval=x, max_derivative_order_eval=1) for t, x in zip(ts, xs_d))
     shape = (128, 128, 128, 3)
+    gen = torch.Generator(device="cuda").manual_seed(7)
     u = D.f_empty(shape, np.float64, "cuda")
     u.copy_(torch.rand(shape[::-1], generator=gen, device="cuda", dtype=torch.float64).permute(3, 2, 1, 0))
     itp = D.NDInterpolation(u, dims)
     orders_all = ((0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1))
-    outs = {o: D.eval_unstructured(itp, derivative_orders=o) for o in orders_all}
-    assert itp.last_kernel.startswith("unstructured")
-    # oracle on a subsample
-    sel = torch.from_numpy(rng.integers(0, n, 100_000)).cuda()
-    xs_h = [x[sel].cpu().numpy() for x in xs_d]
+    sel_h = rng.integers(0, n, 100_000)
+    sel = torch.from_numpy(sel_h).cuda()
+    xs_h = H.counter_points_np(sel_h, ts, 31, np.float64, overshoot=0.01)
+    for d in range(3):   # the device generator and the numpy one agree bit for bit
+        assert np.array_equal(xs_d[d][sel].cpu().numpy(), xs_h[d])
     u_h = u.cpu().numpy()
+    out = D.f_empty((n, 3), np.float64, "cuda")
+    out_s = D.f_empty((n, 3), np.float64, "cuda")
+    worst = 0.0
     for o in orders_all:
+        D.eval_unstructured_(out, itp, derivative_orders=o)
+        assert itp.last_kernel.startswith("unstructured")
         ref = O.evaluate(["bspline"] * 3, ts, u_h, xs_h, degrees=[3] * 3, derivative_orders=o)
-        got = outs[o][sel].cpu().numpy()
-        assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
-    # the cell-sorted plan gives bit-identical results at the original positions
-    for o in ((0, 0, 0), (0, 1, 0)):
-        assert torch.equal(D.eval_unstructured(itp, derivative_orders=o, flags=CELL_SORTED), outs[o])
+        got = out[sel].cpu().numpy()
+        err = np.max(np.abs(got - ref)) / np.max(np.abs(ref))
+        worst = max(worst, err)
+        assert err <= 1e-12, (o, err)
+        # the cell-sorted plan gives bit-identical results at the original positions — all 10^8 of them
+        D.eval_unstructured_(out_s, itp, derivative_orders=o, flags=CELL_SORTED)
+        assert torch.equal(out_s, out), o
+    H.record_observed(worst / 1e-12, worst)
+    # interval indices of the subsample, bit-exact (get_idx, src/interpolation_utils.jl:104-134)
+    for d in range(3):
+        sub = D.BSplineInterpolationDimension(ts[d], 3, t_eval=xs_h[d])
+        assert np.array_equal(sub.idx_eval, O.get_idx("bspline", ts[d], xs_h[d], degree=3))
+    # fused value + gradient == the four separate evaluations (same summation order per slot is not promised: 1e-12)
+    del out_s
+    g = D.eval_unstructured_gradient(itp, flags=CELL_SORTED)
+    for s_, o in enumerate(orders_all):
+        ref = O.evaluate(["bspline"] * 3, ts, u_h, xs_h, degrees=[3] * 3, derivative_orders=o)
+        got = g[..., s_][sel].cpu().numpy()
+        assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref)), o
+    del g
     # partition of unity: a constant control net gives the constant, and zero gradient
     u.fill_(2.0)
     itp.set_u(u)
-    assert float((D.eval_unstructured(itp) - 2.0).abs().max()) <= 1e-12
-    assert float(D.eval_unstructured(itp, derivative_orders=(0, 0, 1)).abs().max()) <= 1e-11
+    D.eval_unstructured_(out, itp)
+    assert float((out - 2.0).abs().max()) <= 1e-12
+    D.eval_unstructured_(out, itp, derivative_orders=(0, 0, 1))
+    assert float(out.abs().max()) <= 1e-11
     itp.close()
 
 
@@ -175,30 +201,50 @@ def test_c4_nurbs_grid_properties(D, torch):
 
 
 # ---- config 5: 5-D linear lookup table u (32^5, 4) Float32, point-sharded ------------------------------------
-def test_c5_multilinear_reproduction_and_sharding(D, torch):
-    rng = np.random.default_rng(5)
+def _c5_setup(D, torch, seed=5):
+    rng = np.random.default_rng(seed)
     ts = [knots(rng, 32, np.float32) for _ in range(5)]
-    n = 50_000_000
-    gen = torch.Generator(device="cuda").manual_seed(11)
-    xs_d = [torch.rand(n, generator=gen, device="cuda") * float(t[-1] - t[0]) + float(t[0]) for t in ts]
-    t_d = [torch.from_numpy(t).cuda() for t in ts]
-    coef = [0.3, -0.2, 0.15, 0.4, -0.1]
     shape = (32,) * 5 + (4,)
+    gen = torch.Generator(device="cuda").manual_seed(11)
     u = D.f_empty(shape, np.float32, "cuda")
-    base = 1.0
-    for d in range(5):
-        view = [1] * 5
-        view[d] = 32
-        base = base + coef[d] * t_d[d].reshape(view)
-    for c in range(4):
-        u[..., c] = (c + 1) * base     # component c is (c+1) times a function that is linear in every axis
+    u.copy_(torch.rand(shape[::-1], generator=gen, device="cuda").permute(*reversed(range(6))))   # random u: every corner matters
+    return rng, ts, u
+
+
+def _c5_check_subsample(D, torch, H, ts, u_h, out, lo, sel_h, orders, seed):
+    """oracle on the global points sel_h (lo <= sel_h < lo + len(out)): values at 1e-5, regenerated coordinates."""
+    xs_h = H.counter_points_np(sel_h, ts, seed, np.float32, overshoot=0.01)
+    ref = O.evaluate(["linear"] * 5, ts, u_h, xs_h, derivative_orders=orders)
+    got = out[torch.from_numpy(sel_h - lo).cuda()].cpu().numpy()
+    err = float(np.max(np.abs(got - ref)) / np.max(np.abs(ref)))
+    assert err <= 1e-5, (orders, err)
+    return err, xs_h
+
+
+def test_c5_random_u_against_oracle_and_sharding(D, torch):
+    """Random u (an affine u is reproduced from ANY cell, so it cannot see a wrong interval or corner order —
+    src/interpolation_utils.jl:116-134, src/interpolation_methods.jl:22-36): value and one first derivative against
+    the oracle on a 10^5-point subsample, interval indices of the subsample bit-exact, plan == no plan bit for bit,
+    index-range shards tile the single-handle result."""
+    from tests import helpers as H
+    rng, ts, u = _c5_setup(D, torch)
+    n, seed = 50_000_000, 41
+    xs_d = H.counter_points_torch(0, n, ts, seed, np.float32, "cuda", overshoot=0.01)
     dims = tuple(D.LinearInterpolationDimension(t, t_eval=x) for t, x in zip(ts, xs_d))
     itp = D.NDInterpolation(u, dims)
+    u_h = u.cpu().numpy()
+    sel_h = rng.integers(0, n, 100_000)
     out = D.eval_unstructured(itp)
-    exp = 1.0 + sum(cf * x for cf, x in zip(coef, xs_d))
-    for c in range(4):
-        assert float((out[:, c] - (c + 1) * exp).abs().max()) <= 2e-5 * (c + 1) * float(exp.abs().max())
+    e0, xs_h = _c5_check_subsample(D, torch, H, ts, u_h, out, 0, sel_h, (0,) * 5, seed)
     assert torch.equal(D.eval_unstructured(itp, flags=CELL_SORTED), out)
+    d3 = D.eval_unstructured(itp, derivative_orders=(0, 0, 1, 0, 0))
+    e1, _ = _c5_check_subsample(D, torch, H, ts, u_h, d3, 0, sel_h, (0, 0, 1, 0, 0), seed)
+    assert torch.equal(D.eval_unstructured(itp, derivative_orders=(0, 0, 1, 0, 0), flags=CELL_SORTED), d3)
+    H.record_observed(max(e0, e1) / 1e-5, max(e0, e1))
+    for d in range(5):
+        assert np.array_equal(xs_d[d][torch.from_numpy(sel_h).cuda()].cpu().numpy(), xs_h[d])
+        sub = D.LinearInterpolationDimension(ts[d], t_eval=xs_h[d])
+        assert np.array_equal(sub.idx_eval, O.get_idx("linear", ts[d], xs_h[d], dtype=np.float32))
     itp.close()
     # index-range sharding: rank r of 4 evaluates its slice with its own handle; the pieces tile the result
     for r in range(4):
@@ -206,3 +252,33 @@ def test_c5_multilinear_reproduction_and_sharding(D, torch):
         it = D.NDInterpolation(u, tuple(D.LinearInterpolationDimension(t, t_eval=x[lo:hi]) for t, x in zip(ts, xs_d)))
         assert torch.equal(D.eval_unstructured(it), out[lo:hi])
         it.close()
+
+
+def test_c5_full_size_4e9_points_in_shards_on_one_gpu(D, torch):
+    """BASELINE configs[4] at its named size, 4*10^9 points, on ONE GPU: the eight index-range shards an 8-GPU job
+    would own (5*10^8 points each, generated on the device from the global index) are evaluated one after the
+    other by one handle; every shard is checked against the oracle on a subsample and through the multilinear
+    partition of unity (the four components of a constant table)."""
+    from tests import helpers as H
+    rng, ts, u = _c5_setup(D, torch)
+    u_h = u.cpu().numpy()
+    n_total, world, seed = 4_000_000_000, 8, 43
+    itp = None
+    worst = 0.0
+    out = None
+    for r in range(world):
+        lo, hi = D.shard_range(n_total, r, world)
+        xs_d = H.counter_points_torch(lo, hi, ts, seed, np.float32, "cuda", overshoot=0.01)
+        if itp is None:
+            itp = D.NDInterpolation(u, tuple(D.LinearInterpolationDimension(t, t_eval=x) for t, x in zip(ts, xs_d)))
+            out = D.f_empty((hi - lo, 4), np.float32, "cuda")
+        else:
+            itp.set_t_eval(xs_d)
+        D.eval_unstructured_(out, itp)
+        sel_h = lo + rng.integers(0, hi - lo, 20_000)
+        err, _ = _c5_check_subsample(D, torch, H, ts, u_h, out, lo, sel_h, (0,) * 5, seed)
+        worst = max(worst, err)
+        assert bool(torch.isfinite(out).all())
+        del xs_d
+    H.record_observed(worst / 1e-5, worst)
+    itp.close()

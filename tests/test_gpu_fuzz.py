@@ -68,8 +68,8 @@ def test_fuzz_grid_fast_vs_generic_vs_oracle(D, seed):
     ref = H.oracle_eval(kinds, ts, u, xs, **kw)
     fast, kern = H.gpu_eval(D, kinds, ts, u, xs, **kw)
     gen, _ = H.gpu_eval(D, kinds, ts, u, xs, flags=GENERIC, **kw)
-    H.assert_close(fast, ref, dtype, factor=8.0)
-    H.assert_close(gen, ref, dtype, factor=8.0)
+    H.assert_close(fast, ref, dtype)
+    H.assert_close(gen, ref, dtype)
 
 
 @pytest.mark.parametrize("seed", range(16))
@@ -83,4 +83,4 @@ def test_fuzz_unstructured_fast_vs_generic_vs_oracle(D, seed):
     ref = H.oracle_eval(kinds, ts, u, xs, **kw)
     for flags in (0, GENERIC, 16):
         got, _ = H.gpu_eval(D, kinds, ts, u, xs, flags=flags, **kw)
-        H.assert_close(got, ref, dtype, factor=8.0)
+        H.assert_close(got, ref, dtype)

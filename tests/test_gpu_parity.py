@@ -70,7 +70,7 @@ def test_basis_function_eval_cache(D, dtype, degree):
     got = dim.basis_function_eval
     assert got.shape == ref.shape == (x.size, degree + 1, max_r + 1)
     for r in range(max_r + 1):
-        H.assert_close(got[:, :, r], ref[:, :, r], dtype, factor=4.0)
+        H.assert_close(got[:, :, r], ref[:, :, r], dtype)
 
 
 # ---- A9-A13: evaluators, unstructured and grid, all kinds ------------------------------------------
@@ -122,7 +122,7 @@ def test_unstructured_parity(D, dtype, flags, case):
             got, _ = H.gpu_eval(D, kinds, ts, u, xs, flags=flags, out=out, **kw)
         else:
             got, _ = H.gpu_eval(D, kinds, ts, u, xs, flags=flags, **kw)
-        H.assert_close(got, ref, dtype, factor=4.0)
+        H.assert_close(got, ref, dtype)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -143,7 +143,7 @@ def test_grid_parity(D, dtype, flags, case):
             got, _ = H.gpu_eval(D, kinds, ts, u, xs, flags=flags, out=out, **kw)
         else:
             got, _ = H.gpu_eval(D, kinds, ts, u, xs, flags=flags, **kw)
-        H.assert_close(got, ref, dtype, factor=4.0)
+        H.assert_close(got, ref, dtype)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -153,17 +153,70 @@ def test_nurbs_parity(D, dtype, flags, n_in, degree, out_dims):
     rng = np.random.default_rng(300 + n_in)
     kinds, degrees = ("bspline",) * n_in, (degree,) * n_in
     ts, u, w = _case(rng, kinds, degrees, (6, 5, 6, 5)[:n_in], out_dims, dtype, nurbs=True)
-    # inside the knot span only: a rational function extrapolated outside it has poles (the
-    # denominator sum(w*B) changes sign), where comparing two roundings is meaningless
+    # inside the knot span (norm-wise bound); outside it the quotient has poles and
+    # test_nurbs_extrapolation_parity applies the point-wise quotient bound instead
     xs = H.zipped_queries(rng, ts, 2000, dtype, outside=False)
     ref = H.oracle_eval(kinds, ts, u, xs, degrees=degrees, weights=w)
     got, _ = H.gpu_eval(D, kinds, ts, u, xs, degrees=degrees, weights=w, flags=flags)
-    H.assert_close(got, ref, dtype, factor=8.0)
+    H.assert_close(got, ref, dtype)
     n_per = {1: 300, 2: 40, 3: 12, 4: 6}[n_in]
     xg = [np.sort(H.query(rng, t, n_per, dtype, outside=False)) for t in ts]
     ref = H.oracle_eval(kinds, ts, u, xg, degrees=degrees, weights=w, grid=True)
     got, _ = H.gpu_eval(D, kinds, ts, u, xg, degrees=degrees, weights=w, grid=True, flags=flags)
-    H.assert_close(got, ref, dtype, factor=8.0)
+    H.assert_close(got, ref, dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("flags", [0, GENERIC])
+@pytest.mark.parametrize("grid", [False, True])
+@pytest.mark.parametrize("n_in,degree,out_dims", [(1, 2, (2,)), (2, 3, ()), (3, 2, ()), (4, 2, ())])
+def test_nurbs_extrapolation_parity(D, dtype, flags, grid, n_in, degree, out_dims):
+    """NURBS OUTSIDE the knot span: the reference evaluates there with the clamped interval
+    (src/interpolation_utils.jl:128-132) and divides (src/interpolation_methods.jl:134-138).  The quotient of two
+    extrapolated polynomials has poles, so the bound is the first-order one for a quotient whose numerator
+    sum(w*B*u) and denominator sum(w*B) are each accurate to TOL norm-wise:
+        |q_gpu - q_ref| * |den_ref| <= TOL * (max|num_ref| + |q_ref| * max|den_ref|)      (point-wise)
+    on every point whose denominator is at least 5 % of the typical one — and those must be > 80 % of the points.
+    Numerator and denominator are also checked on their own: both are plain B-spline contractions (of u*w and of
+    w), evaluated by the same library outside the span and compared with the oracle norm-wise at TOL."""
+    rng = np.random.default_rng(700 + 10 * n_in + degree)
+    kinds, degrees = ("bspline",) * n_in, (degree,) * n_in
+    ts, u, w = _case(rng, kinds, degrees, (6, 5, 6, 5)[:n_in], out_dims, dtype, nurbs=True)
+    def pts(t, n):   # 60 % inside the span, 40 % up to 10 % of the span outside it, plus both ends of the span
+        span = float(t[-1] - t[0])
+        k = int(0.4 * n)
+        side = rng.random(k) < 0.5
+        out = np.where(side, t[0] - rng.random(k) * 0.1 * span, t[-1] + rng.random(k) * 0.1 * span)
+        x = np.concatenate([rng.uniform(t[0], t[-1], n - k - 2), out, [t[0], t[-1]]])
+        rng.shuffle(x)
+        return x.astype(dtype)
+    if grid:
+        n_per = {1: 300, 2: 40, 3: 12, 4: 6}[n_in]
+        xs = [np.sort(pts(t, n_per)) for t in ts]
+    else:
+        xs = [pts(t, 2000) for t in ts]
+    kw = dict(degrees=degrees, grid=grid)
+    wshape = w.shape + (1,) * len(out_dims)
+    uw = (u * w.reshape(wshape)).astype(dtype)
+    num_ref = H.oracle_eval(kinds, ts, uw, xs, **kw)
+    den_ref = H.oracle_eval(kinds, ts, w, xs, **kw)
+    q_ref = H.oracle_eval(kinds, ts, u, xs, weights=w, **kw)
+    num_gpu, _ = H.gpu_eval(D, kinds, ts, uw, xs, flags=flags, **kw)
+    den_gpu, _ = H.gpu_eval(D, kinds, ts, w, xs, flags=flags, **kw)
+    H.assert_close(num_gpu, num_ref, dtype)
+    H.assert_close(den_gpu, den_ref, dtype)
+    q_gpu, _ = H.gpu_eval(D, kinds, ts, u, xs, weights=w, flags=flags, **kw)
+    tol = H.TOL[np.dtype(dtype)]
+    den_b = den_ref.reshape(den_ref.shape + (1,) * len(out_dims)).astype(np.float64)
+    s_num, s_den = float(np.max(np.abs(num_ref))), float(np.max(np.abs(den_ref)))
+    ok = np.abs(den_b) >= 0.05 * float(np.median(np.abs(den_ref)))
+    ok = np.broadcast_to(ok, q_ref.shape)
+    assert ok.mean() > 0.8, ok.mean()
+    lhs = np.abs(q_gpu.astype(np.float64) - q_ref.astype(np.float64)) * np.abs(den_b)
+    rhs = tol * (s_num + np.abs(q_ref.astype(np.float64)) * s_den)
+    H.record_observed(float(np.max((lhs / rhs)[ok])), float(np.max((lhs / rhs)[ok])) * tol)
+    assert np.all(lhs[ok] <= rhs[ok]), float(np.max((lhs / rhs)[ok]))
+    assert np.array_equal(np.isnan(q_gpu), np.isnan(q_ref))
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -187,10 +240,10 @@ def test_grid_split_4d_matches_oracle_and_pencil(D, dtype, degree, nurbs, out_di
     ref = H.oracle_eval(kinds, ts, u, xg, **kw)
     got, kernel = H.gpu_eval(D, kinds, ts, u, xg, **kw)
     assert kernel.startswith("grid_split"), kernel
-    H.assert_close(got, ref, dtype, factor=8.0)
+    H.assert_close(got, ref, dtype)
     gen, kernel_g = H.gpu_eval(D, kinds, ts, u, xg, flags=GENERIC, **kw)
     assert kernel_g == "generic_grid"
-    H.assert_close(got, gen, dtype, factor=8.0)
+    H.assert_close(got, gen, dtype)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -216,7 +269,7 @@ def test_grid_split_4d_with_constant_selector_axis(D, dtype, const_axis, degree,
     ref = H.oracle_eval(kinds, ts, u, xg, **kw)
     got, kernel = H.gpu_eval(D, kinds, ts, u, xg, **kw)
     assert kernel.startswith("grid_split") and "selector" in kernel, kernel
-    H.assert_close(got, ref, dtype, factor=8.0)
+    H.assert_close(got, ref, dtype)
     # slice equivalence: fix the Constant axis at the node the reference's index rule picks
     tc = ts[const_axis]
     j = np.clip(np.searchsorted(tc, xg[const_axis], side="right"), 1, tc.size - 1) - 1
@@ -227,7 +280,7 @@ def test_grid_split_4d_with_constant_selector_axis(D, dtype, const_axis, degree,
         ws = None if w is None else np.take(w, j[gi], axis=const_axis)
         sl = H.oracle_eval(("bspline",) * 3, [ts[d] for d in rest], us, [xg[d] for d in rest],
                            degrees=(degree,) * 3, weights=ws, grid=True)
-        H.assert_close(np.take(got, gi, axis=const_axis), sl, dtype, factor=8.0)
+        H.assert_close(np.take(got, gi, axis=const_axis), sl, dtype)
 
 
 def test_cached_idx_path_matches(D):
@@ -335,19 +388,19 @@ def test_golden_scipy_vectors_on_gpu(D, golden):
         t, u, x = (golden[f"bs1d_p{p}_{k}"] for k in "tux")
         for r in range(4):
             got, _ = H.gpu_eval(D, ["bspline"], [t], u, [x], degrees=[p], derivative_orders=[r])
-            H.assert_close(got, golden[f"bs1d_p{p}_r{r}"], np.float64, factor=20.0)
+            H.assert_close(got, golden[f"bs1d_p{p}_r{r}"], np.float64)
     ta, tb, u, xa, xb = (golden[f"bs2d_{k}"] for k in ("ta", "tb", "u", "xa", "xb"))
     for ra, rb in ((0, 0), (1, 0), (0, 1), (1, 1), (2, 1)):
         kw = dict(degrees=[2, 3], derivative_orders=[ra, rb])
         got, _ = H.gpu_eval(D, ["bspline"] * 2, [ta, tb], u, [xa, xb], grid=True, **kw)
-        H.assert_close(got, golden[f"bs2d_grid_r{ra}{rb}"], np.float64, factor=20.0)
+        H.assert_close(got, golden[f"bs2d_grid_r{ra}{rb}"], np.float64)
         got, _ = H.gpu_eval(D, ["bspline"] * 2, [ta, tb], u, [xa, xb], **kw)
-        H.assert_close(got, golden[f"bs2d_unst_r{ra}{rb}"], np.float64, factor=20.0)
+        H.assert_close(got, golden[f"bs2d_unst_r{ra}{rb}"], np.float64)
     for nd in (2, 3, 5):
         ts = [golden[f"lin{nd}d_t{d}"] for d in range(nd)]
         xs = [golden[f"lin{nd}d_x{d}"] for d in range(nd)]
         got, _ = H.gpu_eval(D, ["linear"] * nd, ts, golden[f"lin{nd}d_u"], xs)
-        H.assert_close(got, golden[f"lin{nd}d_val"], np.float64, factor=20.0)
+        H.assert_close(got, golden[f"lin{nd}d_val"], np.float64)
 
 
 # ---- interface behaviour ---------------------------------------------------------------------------
@@ -610,12 +663,12 @@ def test_nurbs_weights_with_constant_axis(D):
     ref = H.oracle_eval(kinds, ts, u, xg, degrees=degrees, weights=w, grid=True)
     for flags in (0, GENERIC):
         got, kern = H.gpu_eval(D, kinds, ts, u, xg, degrees=degrees, weights=w, grid=True, flags=flags)
-        H.assert_close(got, ref, np.float64, factor=8.0)
+        H.assert_close(got, ref, np.float64)
     j = np.where(xg[2] >= ts[2][-1], len(ts[2]), O.get_idx("constant", ts[2], xg[2])) - 1
     for k in (0, len(xg[2]) // 2, len(xg[2]) - 1):
         sl = H.oracle_eval(("bspline",) * 3, [ts[0], ts[1], ts[3]], u[:, :, j[k], :], [xg[0], xg[1], xg[3]],
                            degrees=(2, 2, 2), weights=w[:, :, j[k], :], grid=True)
-        H.assert_close(got[:, :, k, :], sl, np.float64, factor=8.0)
+        H.assert_close(got[:, :, k, :], sl, np.float64)
 
 
 # ---- fused value + gradient (beyond the reference: SURVEY.md §8f rank 1) ---------------------------------
@@ -635,7 +688,7 @@ def test_fused_gradient_equals_separate_evaluations(D, dtype, flags, case):
     for s in range(n + 1):
         orders = tuple(1 if d + 1 == s else 0 for d in range(n))
         ref = H.oracle_eval(kinds, ts, u, xs, degrees=degrees, derivative_orders=orders)
-        H.assert_close(g[..., s], ref, dtype, factor=4.0)
+        H.assert_close(g[..., s], ref, dtype)
     itp.close()
 
 
