@@ -2,15 +2,22 @@
 """bench.py — headline benchmark of the B200 evaluation engine (BASELINE.json metric:
 Gpoints/s for eval_unstructured / eval_grid!, fraction of the HBM roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c5] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4|c4b|c5] [--impl reference]
+                    [--only-headline]
 
-A "step" is one pass of the hot path over one batch of synthetic input:
-  c2 (default, BASELINE configs[1]): 3-D trilinear scalar field u = 256^3 Float32, eval_grid!
-      onto a 512^3 t_eval grid with cached per-axis indices/weights, a fresh `u` each step.
-  c1 / c3 / c5: the unstructured configs; c3/c5 at a reduced point count unless --full.
-Multi-GPU (torchrun, one rank per GPU): grids are sharded by slab along the last axis, point
-lists by contiguous index range, u and knots replicated, no data-path collective; the global
-problem grows with N (weak scaling): c2 at N GPUs is a 512 x 512 x (512*N) grid.
+A "step" is one pass of the hot path over one batch of synthetic input.  The headline (`value`) is
+  c2 (BASELINE configs[1]): 3-D trilinear scalar field u = 256^3 Float32, eval_grid! onto a 512^3 t_eval
+      grid with cached per-axis indices/weights, a fresh `u` each step.
+The same JSON line also carries every other BASELINE config at its named size:
+  N = 1:  "configs": {c1, c3, c3_sorted, c3_plan_order, c3_gradient, c4, c4b, c5, c5_sorted, c5_plan_order}
+          (c3: 10^8 points; c5: 5*10^8 points = one GPU's share of the 4*10^9-point config on 8 GPUs);
+  N > 1:  "point_sharded": {c5, c3} — the point list sharded by contiguous index range over the N ranks (weak
+          scaling: 5*10^8 / 10^8 points per GPU, so c5 at N = 8 IS the named 4*10^9-point config), timed without
+          and with the NCCL all-gather of the outputs (dind_allgather_out), max over ranks.
+Multi-GPU (torchrun, one rank per GPU): grids are sharded by slab along the last axis, point lists by contiguous
+index range, u and knots replicated, no data-path collective.  Weak scaling of the grid headline: the global last
+axis is N sweeps over the same knot span (a legitimate unsorted t_eval), so every rank evaluates exactly the N = 1
+problem — same u extent, same density, same algorithmic bytes.
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference
 (oracle/, OpenMP over all host cores: the reference itself is Julia and cannot run here).
@@ -31,9 +38,23 @@ sys.path.insert(0, ROOT)
 
 METRIC = "Gpoints/s"
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-# `ncu --set full` captures (profiles/r1_<workload>.md); None where no capture exists.
-NCU_TRAFFIC = {"c2": 546_288_128, "c4": 3_386_374_000, "c1": 16_083_456, "c3": 1_015_403_008, "c5": 184_760_204_000}
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, parsed from the newest committed
+    `ncu --set full` summary profiles/r<round>_<key>.md (scripts/ncu_summary.py wrote it); None without a capture."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_{key}.md")), reverse=True)
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for fn in files:
+        tot, seen = 0.0, 0
+        for line in open(fn):
+            m = re.match(r"\| dram__bytes_(read|write)\.sum \| ([0-9.,]+) \| (\w+) \|", line)
+            if m:
+                tot += float(m.group(2).replace(",", "")) * unit.get(m.group(3), 1.0)
+                seen += 1
+                if seen == 2:   # the first kernel section = the dominant kernel
+                    return {"bytes": int(tot), "source": os.path.relpath(fn, ROOT)}
+    return None
 
 
 def measured_peaks():
@@ -82,14 +103,9 @@ class Grid(Workload):
         rng = np.random.default_rng(1234)
         nd = len(self.n_u)
         self.ts = [knots_1d(rng, self.n_knots(d), self.dtype) for d in range(nd)]
-        # global grid: the last axis has n_grid[-1] * world points, rank r owns slab r
-        self.t_evals = []
-        for d, (t, g) in enumerate(zip(self.ts, self.n_grid)):
-            if d == nd - 1:
-                full = np.linspace(t[0], t[-1], g * world).astype(self.dtype)
-                self.t_evals.append(full[rank * g:(rank + 1) * g])
-            else:
-                self.t_evals.append(np.linspace(t[0], t[-1], g).astype(self.dtype))
+        # global grid: the last axis has n_grid[-1] * world points = `world` sweeps over the knot span (t_eval need not
+        # be sorted), rank r owns slab r = one sweep: every rank evaluates exactly the N = 1 problem
+        self.t_evals = [np.linspace(t[0], t[-1], g).astype(self.dtype) for t, g in zip(self.ts, self.n_grid)]
 
     def make_dims(self, D, t_evals):
         dims = []
@@ -425,16 +441,17 @@ def run_gpu(args, wl, rank, world, local_rank):
     pts_step_all = wl.points_per_step() * world
     value = pts_step_all / (ms_per_step * 1e-3) / 1e9
     peaks, peak_src = measured_peaks()
-    achieved = wl.alg_bytes() / (ms_per_step * 1e-3) / 1e9     # per GPU: one launch per step per rank
+    traffic = ncu_traffic(wl.key + ("_sorted" if args.sorted else ""))
+    achieved = wl.alg_bytes() / (ms_per_step * 1e-3) / 1e9     # per GPU: one launch per step per rank, the bytes that rank touches
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": "Gpoints/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": wl.dtype_name, "data": "synthetic",
         "config": {"workload": wl.name, "points_per_step_per_gpu": wl.points_per_step(),
                    "sharding": (("slab along the last grid axis" if wl.grid else "contiguous index range") + ", u/knots replicated, no collective"
-                                + (f"; weak scaling: u fixed, the global grid's last axis has {world}x the points, so every rank writes the same number of "
-                                   f"outputs but samples its part of the last axis {world}x more densely (fewer window updates per output: per-GPU "
-                                   f"throughput rises slightly with N)" if wl.grid and world > 1 else "")),
+                                + (f"; weak scaling: the global grid's last axis is {world} sweeps over the knot span ({world}x the points), rank r "
+                                   f"owns sweep r — every rank evaluates exactly the N = 1 problem (same u extent, density and algorithmic bytes)"
+                                   if wl.grid and world > 1 else "")),
                    "l2": f"working set exceeds L2 (126 MB): output streamed, u rotates over {wl.n_u_buffers} buffers" if wl.grid else "t_eval + out exceed L2",
                    "kernel": kernel, "first_call_ms_incl_cache_build": round(first_call_ms, 3), "cache_build": cache_build, "gradient": args.gradient, "all_gather_outputs": bool(args.gather and world > 1), "point_order": ("iid random, evaluated through the cell-sorted plan" + (", output left in plan order" if args.plan_order else "") if args.sorted else "iid random") if not wl.grid else "grid"},
         "e2e": {"value": round(pts_step_all / (e2e_ms * 1e-3) / 1e9, 4), "unit": "Gpoints/s",
@@ -443,7 +460,8 @@ def run_gpu(args, wl, rank, world, local_rank):
                 "synchronous_calls_value": (round(pts_step_all / (e2e_sync_ms * 1e-3) / 1e9, 4) if wl.grid else None)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": NCU_TRAFFIC.get(wl.key), "peak_source": peak_src,
+                     "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": (traffic or {}).get("bytes"),
+                     "traffic_source": (traffic or {}).get("source"), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": wl.alg_bytes()},
         "clocks": clocks.summary(),
     }

@@ -81,7 +81,7 @@ def main():
         assert np.array_equal(xs_d[d][sel_d].cpu().numpy(), xs_h[d])
     # --- the shards tile a single-handle evaluation of the same global points (bit for bit)
     single = D.NDInterpolation(u, tuple(D.LinearInterpolationDimension(t, t_eval=x) for t, x in zip(ts, xs_h)), device=local)
-    assert np.array_equal(np.asarray(D.eval_unstructured(single)), got)
+    assert np.array_equal(D.eval_unstructured(single).cpu().numpy(), got)
     for d in range(5):
         assert np.array_equal(single.interp_dims[d].idx_eval, O.get_idx("linear", ts[d], xs_h[d], dtype=np.float32))
     single.close()
@@ -125,6 +125,7 @@ def main():
 
     # --- slab-sharded eval_grid: 3-D trilinear u 64^3 -> 128 x 128 x (16 * world + 3) grid (uneven slabs)
     g_last = 16 * world + 3
+    rng = np.random.default_rng(17)   # fresh stream: the draws above depend on the rank's shard size
     tg = [np.cumsum(0.5 + rng.random(64)).astype(np.float32) for _ in range(3)]
     ug = rng.random((64, 64, 64)).astype(np.float32)
     xg = [np.linspace(t[0], t[-1], n).astype(np.float32) for t, n in zip(tg, (128, 128, g_last))]
@@ -139,7 +140,8 @@ def main():
     if not args.no_gather:
         gathered = D.gather_grid(slab, 3, g_last, interp=itg)
         torch.cuda.synchronize()
-        assert torch.equal(gathered, ref_grid)
+        bad = (gathered != ref_grid).flatten(0, 1).any(dim=0).nonzero().flatten().tolist()
+        assert not bad, f"rank {rank}: gathered grid differs in last-axis planes {bad} (own slab {glo}:{ghi})"
     itg.close()
     whole.close()
 

@@ -34,6 +34,9 @@ def test_point_sharded_c5_and_slab_grid_with_nccl_allgather():
     if full and world < 8:
         cmd.append("--no-gather")
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"multi_gpu_worker_n{world}.log"), "w") as f:
+        f.write(p.stdout + "\n---- stderr ----\n" + p.stderr)
     tail = (p.stdout + p.stderr)[-4000:]
     assert p.returncode == 0, tail
     assert "MULTI_GPU_REPORT" in p.stdout, tail
