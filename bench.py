@@ -469,6 +469,240 @@ def run_gpu(args, wl, rank, world, local_rank):
     return line
 
 
+# ---- the other BASELINE configs at their named sizes, in the same JSON line ---------------------------------------
+FMA_PEAK_TFMA = {"f64": 17.6, "f32": 32.3}   # register-resident FMA microbenchmark on B200 (scripts/microbench_fma.cu; profiles/r2_microbench.txt)
+C3_FP64_OPS_PER_POINT = 378                  # 285 DFMA + 51 DADD + 42 DMUL per point and evaluation (ncu instruction mix)
+
+
+def _time_steps(torch, dist, stream, world, fn, steps, warmup):
+    """W warm-ups, then K steps between CUDA events on the launching stream; barrier + synchronize on both sides."""
+    for i in range(warmup):
+        fn(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def _max_over_ranks(torch, dist, world, dev, vals):
+    t = torch.tensor(vals, device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def _entry(wl, ms, n_points_all, alg_bytes_rank, launches, kernel, extra=None):
+    peaks, _ = measured_peaks()
+    achieved = alg_bytes_rank / (ms * 1e-3) / 1e9
+    e = {"value": round(n_points_all / (ms * 1e-3) / 1e9, 3), "unit": "Gpoints/s", "ms_per_step": round(ms, 4),
+         "roofline": {"bound": "hbm", "frac": round(achieved / peaks["hbm_gbs"], 4), "achieved": round(achieved, 1),
+                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "algorithmic_bytes": int(alg_bytes_rank)},
+         "kernel": kernel, "gpu_launches_per_step": launches, "dtype": wl.dtype_name}
+    if extra:
+        e.update(extra)
+    return e
+
+
+def bench_unstructured_family(D, torch, dist, wl, rank, world, local_rank, steps, warmup, modes, gather=False):
+    """One point-sharded unstructured workload (weak scaling: wl.n_points per rank), several evaluation modes over the
+    same device-resident points: iid order, through the cell-sorted plan (original order / plan order), fused gradient.
+    Returns {mode: entry}.  With `gather`, also the step followed by the NCCL all-gather of the outputs."""
+    dev = f"cuda:{local_rank}"
+    stream = torch.cuda.current_stream()
+    tdt = torch.float32 if wl.dtype == np.float32 else torch.float64
+    wl.build(rank, world)
+    n_total = wl.n_points * world
+    lo, hi = D.shard_range(n_total, rank, world)
+    n = hi - lo
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(2000 + rank)
+    xs = [torch.rand(n, generator=gen, device=dev, dtype=tdt) * float(t[-1] - t[0]) + float(t[0]) for t in wl.ts]
+    mk = {"linear": lambda t, p, x: D.LinearInterpolationDimension(t, t_eval=x),
+          "bspline": lambda t, p, x: D.BSplineInterpolationDimension(t, p, t_eval=x, max_derivative_order_eval=1)}
+    dims = tuple(mk[k](t, p, x) for k, t, p, x in zip(wl.kinds, wl.ts, wl.degrees, xs))
+    shape = tuple(wl.n_u)
+    n_in = len(wl.kinds)
+    ud = D.f_empty(shape, wl.dtype, dev)
+    gen_u = torch.Generator(device=dev)
+    gen_u.manual_seed(77)                       # u replicated: the same table on every rank
+    ud.copy_(torch.rand(shape[::-1], generator=gen_u, device=dev, dtype=tdt).permute(*reversed(range(len(shape)))))
+    itp = D.NDInterpolation(ud, dims, device=local_rank, stream=stream.cuda_stream)
+    out = D.f_empty((n,) + shape[n_in:], wl.dtype, dev)
+    esz = np.dtype(wl.dtype).itemsize
+    n_comp = int(np.prod(shape[n_in:])) if len(shape) > n_in else 1
+    u_bytes = int(np.prod(shape)) * esz
+    res = {}
+    FL = {"iid": 1, "sorted": 1 | 16, "plan_order": 1 | 16 | 32}
+    for mode in modes:
+        extra = {"points_per_gpu": n, "point_order": {"iid": "iid random", "sorted": "iid random, evaluated through the cell-sorted plan, results in original order",
+                                                      "plan_order": "iid random, evaluated through the cell-sorted plan, results left in plan order",
+                                                      "gradient": "value + all first partials in one pass through the cell-sorted plan"}[mode]}
+        if mode == "gradient":
+            gout = D.f_empty((n,) + shape[n_in:] + (n_in + 1,), wl.dtype, dev)
+            fn = lambda i: D.eval_unstructured_gradient(itp, gout, flags=1 | 16)
+            alg = n * (n_in + n_comp * (n_in + 1)) * esz + u_bytes      # SURVEY.md §8d: 120 B/pt for config 3
+        else:
+            fn = lambda i, f=FL[mode]: D.eval_unstructured_(out, itp, flags=f)
+            alg = n * (n_in + n_comp) * esz + u_bytes
+        if mode != "iid":
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            itp.build_caches(grid=False, flags=1 | 16)
+            torch.cuda.synchronize()
+            extra["plan_build_ms_first"] = round((time.perf_counter() - t0) * 1e3, 3)
+        l0 = itp.launch_count
+        fn(0)
+        per_step = itp.launch_count - l0
+        ms = _time_steps(torch, dist, stream, world, fn, steps, warmup)
+        kernel = itp.last_kernel
+        (ms,) = _max_over_ranks(torch, dist, world, dev, [ms])
+        if wl.key == "c3":
+            evals = (n_in + 1) if mode == "gradient" else 1
+            fma_bound = FMA_PEAK_TFMA["f64"] * 1e12 / (C3_FP64_OPS_PER_POINT * evals) / 1e9   # Gpoints/s per GPU
+            extra["roofline_fma"] = {"bound": "fp64 pipe", "peak_Gpoints_per_s_per_gpu": round(fma_bound, 1),
+                                     "frac": round(n / (ms * 1e-3) / 1e9 / fma_bound, 4),
+                                     "note": "378 FP64 operations per point and evaluation at the measured 17.6 T/s (DESIGN.md §6)"}
+        res[mode] = _entry(wl, ms, n_total, alg, per_step, kernel, extra)
+        if mode == "gradient":
+            del gout
+    if gather and world > 1:
+        # the optional NCCL all-gather of the outputs (dind_allgather_out), after the kernel, never inside it
+        full = D.gather_unstructured(out, n_total, interp=itp)     # sets up the communicator
+        del full
+        torch.cuda.empty_cache()
+        fullbuf = [None]
+
+        def fn_g(i):
+            D.eval_unstructured_(out, itp, flags=1)
+            fullbuf[0] = None
+            fullbuf[0] = D.gather_unstructured(out, n_total, interp=itp)
+        ms_g = _time_steps(torch, dist, stream, world, fn_g, max(2, min(steps, 5)), 2)
+        fn_e = lambda i: D.eval_unstructured_(out, itp, flags=1)
+        ms_e = _time_steps(torch, dist, stream, world, fn_e, max(2, min(steps, 5)), 1)
+        ms_g, ms_e = _max_over_ranks(torch, dist, world, dev, [ms_g, ms_e])
+        recv = (n_total - n) * n_comp * esz
+        res["iid"]["with_allgather"] = {
+            "value": round(n_total / (ms_g * 1e-3) / 1e9, 3), "ms_per_step": round(ms_g, 3),
+            "allgather_ms": round(ms_g - ms_e, 3), "bytes_received_per_gpu": int(recv),
+            "busbw_GBps": round(recv / max(ms_g - ms_e, 1e-6) / 1e6, 1),
+            "what": f"dind_allgather_out: {n_comp} ncclAllGather calls (one per component column) in one NCCL group, straight into the "
+                    f"(n_total, {n_comp}) result; NVLink/NVSwitch bound"}
+        fullbuf[0] = None
+    itp.close()
+    del xs, out, ud
+    torch.cuda.empty_cache()
+    return res
+
+
+def bench_grid_config(D, torch, dist, wl, rank, world, local_rank, steps, warmup):
+    dev = f"cuda:{local_rank}"
+    stream = torch.cuda.current_stream()
+    tdt = torch.float32 if wl.dtype == np.float32 else torch.float64
+    wl.build(rank, world)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3000 + rank)
+    rev = tuple(reversed(range(len(wl.n_u))))
+
+    def to_dev(a):
+        t = D.f_empty(a.shape, wl.dtype, dev)
+        t.copy_(torch.from_numpy(np.ascontiguousarray(a)).to(dev))
+        return t
+    dims = wl.make_dims(D, [to_dev(x) for x in wl.t_evals])
+    u_bufs = []
+    for _ in range(wl.n_u_buffers):
+        ub = D.f_empty(wl.n_u, wl.dtype, dev)
+        ub.copy_(torch.rand(wl.n_u[::-1], generator=gen, device=dev, dtype=tdt).permute(*rev))
+        u_bufs.append(ub)
+    cache = None
+    if wl.nurbs:
+        wts = D.f_empty(wl.n_u, wl.dtype, dev)
+        wts.copy_((torch.rand(wl.n_u[::-1], generator=gen, device=dev, dtype=tdt) + 0.5).permute(*rev))
+        cache = D.NURBSWeights(wts)
+    itp = D.NDInterpolation(u_bufs[0], dims, cache=cache, device=local_rank, stream=stream.cuda_stream)
+    out = D.f_empty(wl.n_grid, wl.dtype, dev)
+
+    def fn(i):
+        itp.set_u(u_bufs[i % len(u_bufs)])
+        D.eval_grid_(out, itp, flags=1)
+    fn(0)
+    l0 = itp.launch_count
+    fn(1)
+    per_step = itp.launch_count - l0
+    ms = _time_steps(torch, dist, stream, world, fn, steps, warmup)
+    (ms,) = _max_over_ranks(torch, dist, world, dev, [ms])
+    e = _entry(wl, ms, wl.points_per_step() * world, wl.alg_bytes(), per_step, itp.last_kernel,
+               {"grid": list(wl.n_grid), "u": list(wl.n_u)})
+    itp.close()
+    del out, u_bufs
+    torch.cuda.empty_cache()
+    return e
+
+
+def run_all_configs(args, rank, world, local_rank):
+    """Every BASELINE config other than the headline, at its named size (module docstring)."""
+    import torch
+    import torch.distributed as dist
+
+    import dind_b200 as D
+    K, W = max(3, min(args.steps, 10)), 3
+    if world == 1:
+        cfg = {}
+        r = bench_unstructured_family(D, torch, dist, C1(), rank, world, local_rank, max(K, 20), 5, ["iid"])
+        cfg["c1"] = r["iid"]
+        r = bench_unstructured_family(D, torch, dist, C3(100_000_000), rank, world, local_rank, K, W, ["iid", "sorted", "plan_order", "gradient"])
+        cfg.update({"c3": r["iid"], "c3_sorted": r["sorted"], "c3_plan_order": r["plan_order"], "c3_gradient": r["gradient"]})
+        cfg["c4"] = bench_grid_config(D, torch, dist, C4(), rank, world, local_rank, K, W)
+        cfg["c4b"] = bench_grid_config(D, torch, dist, C4b(), rank, world, local_rank, K, W)
+        r = bench_unstructured_family(D, torch, dist, C5(500_000_000), rank, world, local_rank, max(3, K // 2), 2, ["iid"])
+        cfg["c5"] = r["iid"]
+        r = bench_unstructured_family(D, torch, dist, C5(100_000_000), rank, world, local_rank, K, W, ["sorted", "plan_order"])
+        cfg.update({"c5_sorted": r["sorted"], "c5_plan_order": r["plan_order"]})
+        for k, v in cfg.items():
+            t = ncu_traffic(k)
+            v["roofline"]["traffic"] = t["bytes"] if t else None
+            if t:
+                v["roofline"]["traffic_source"] = t["source"]
+        return "configs", cfg
+    ps = {}
+    r = bench_unstructured_family(D, torch, dist, C5(500_000_000), rank, world, local_rank, max(3, K // 2), 2, ["iid"], gather=True)
+    ps["c5"] = r["iid"]
+    ps["c5"]["note"] = (f"{world} x 5e8 points sharded by contiguous index range (at 8 GPUs: BASELINE configs[4], 4e9 points), u (32^5, 4) replicated, "
+                        "no collective in the evaluation; `with_allgather` adds dind_allgather_out of the (n_total, 4) Float32 output")
+    r = bench_unstructured_family(D, torch, dist, C5(100_000_000), rank, world, local_rank, K, W, ["sorted", "plan_order"])
+    ps["c5_sorted"], ps["c5_plan_order"] = r["sorted"], r["plan_order"]
+    r = bench_unstructured_family(D, torch, dist, C3(100_000_000), rank, world, local_rank, K, W, ["iid", "sorted", "plan_order"], gather=True)
+    ps["c3"], ps["c3_sorted"], ps["c3_plan_order"] = r["iid"], r["sorted"], r["plan_order"]
+    return "point_sharded", ps
+
+
+def bind_to_gpu_cpus(local_rank):
+    """Pin this rank to the CPUs NVML reports as local to its GPU (same NUMA node / PCIe root), BEFORE any pinned host
+    buffer is allocated: the e2e leg streams 600 MB per step through host memory, and with 8 ranks on a two-socket box
+    remote-socket buffers halve the copy bandwidth.  Best effort: returns a description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"gpu-local cpus ({len(allowed)} of {n_cpu})"
+        return "unchanged (no gpu-local cpu in the allowed set)"
+    except Exception as e:   # noqa: BLE001
+        return f"unchanged ({type(e).__name__})"
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -562,6 +796,7 @@ def main():
     ap.add_argument("--full", action="store_true", help="full-size point counts for c3 / c5")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink c2 (debugging only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-headline", action="store_true", help="skip the other BASELINE configs (`configs` / `point_sharded`)")
     ap.add_argument("--no-cache-build", action="store_true", help="skip the separate timing of cache construction")
     ap.add_argument("--gradient", choices=["fused", "separate"], default=None,
                     help="unstructured workloads: a step evaluates value + all first partials (one fused pass, or N_in+1 calls)")
@@ -583,10 +818,19 @@ def main():
 
     import torch
     import torch.distributed as dist
+    affinity = None
     if world > 1:
+        affinity = bind_to_gpu_cpus(local_rank)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     line = run_gpu(args, wl, rank, world, local_rank)
+    line["config"]["cpu_affinity"] = affinity
+    if not args.only_headline and args.workload == "c2":
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        key, val = run_all_configs(args, rank, world, local_rank)
+        line[key] = val
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_sample(make_workload(args))
