@@ -387,6 +387,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
             CUDA_TRY(plan_sort_points<T>(P, (uint32_t*)h->plan_perm.p, ts, cells, cell_bits, h->plan_scratch.p, &scratch_bytes, h->stream));
             h->launches += 2 + N;
             h->plan_valid = true;
+            h->plan_items_valid = false;
             h->plan_buckets_valid = false;
             h->plan_n = n_points;
         }
@@ -443,6 +444,38 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         }
         P.u_aos = (const T*)h->u_aos.p;
     }
+    // cell-sorted plan: the work-item schedule of the tile kernels (<= pts consecutive points of one cell per thread)
+    if (use_aos && P.cells) {
+        const int pts = tile_points_per_item<T>(P, gradient);
+        if (pts > 0) {
+            if (!h->plan_items_valid || h->plan_items_pts != pts) {
+                size_t sb = 0;
+                CUDA_TRY(plan_build_items(nullptr, n_points, pts, nullptr, nullptr, nullptr, &sb, h->stream));
+                CUDA_TRY(h->plan_scratch.ensure(sb));
+                sb = h->plan_scratch.cap;
+                int64_t n_items = 0;
+                CUDA_TRY(plan_build_items(P.cells, n_points, pts, nullptr, &n_items, h->plan_scratch.p, &sb, h->stream));
+                CUDA_TRY(h->plan_items.ensure((size_t)(n_items + 1) * sizeof(uint32_t)));
+                CUDA_TRY(plan_build_items(P.cells, n_points, pts, (uint32_t*)h->plan_items.p, &n_items, h->plan_scratch.p, &sb, h->stream));
+                h->plan_n_items = n_items;
+                h->plan_items_pts = pts;
+                P.items = (const uint32_t*)h->plan_items.p;
+                P.n_items = n_items;
+                CUDA_TRY(h->plan_item_cells.ensure((size_t)n_items * sizeof(uint32_t)));
+                T* it[MAXN];
+                for (int d = 0; d < N; ++d) {
+                    CUDA_TRY(h->plan_item_t[d].ensure((size_t)n_items * pts * sizeof(T)));
+                    it[d] = (T*)h->plan_item_t[d].p;
+                }
+                CUDA_TRY(plan_item_layout<T>(P, pts, (uint32_t*)h->plan_item_cells.p, it, h->stream));
+                h->plan_items_valid = true;
+                h->launches += 5;
+            }
+            P.items = (const uint32_t*)h->plan_items.p;
+            P.n_items = h->plan_n_items;
+            P.item_pts = pts;
+        }
+    }
     if (flags & FLAG_BUILD_ONLY) {
         if (!(flags & DIND_FLAG_ASYNC)) CUDA_TRY(cudaStreamSynchronize(h->stream));
         return DIND_OK;
@@ -470,6 +503,12 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
             name = "gradient_by_separate_evaluations";
             handled = true;
         }
+    }
+    if (use_aos && !handled && P.items) {
+        EvalParams<T> Q = P;   // the tile kernels read the item-major copies of the plan's inputs
+        Q.cells = (const uint32_t*)h->plan_item_cells.p;
+        for (int d = 0; d < N; ++d) Q.dim[d].t_eval = (const T*)h->plan_item_t[d].p;
+        handled = try_eval_fast_tile<T>(Q, gradient, h->stream, &name, &err, &nlaunch);
     }
     if (use_aos && !handled) handled = try_eval_fast_unstructured_aos<T>(P, h->stream, &name, &err, &nlaunch);
     if (split && !handled) {
@@ -639,7 +678,8 @@ int dind_destroy(dind_handle_t h) {
     if (h->ev_kernel) cudaEventDestroy(h->ev_kernel);
     for (int i = 0; i < 2; ++i) if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
     comm_release(h);
-    h->plan_perm.release(); h->plan_stage.release(); h->plan_scratch.release(); h->plan_slot2.release(); h->plan_dest2.release(); h->plan_cells.release();
+    h->plan_perm.release(); h->plan_stage.release(); h->plan_scratch.release(); h->plan_slot2.release(); h->plan_dest2.release(); h->plan_cells.release(); h->plan_items.release(); h->plan_item_cells.release();
+    for (int d = 0; d < MAXN; ++d) h->plan_item_t[d].release();
     for (int d = 0; d < MAXN; ++d) h->plan_t[d].release();
     delete h;
     return DIND_OK;

@@ -174,6 +174,11 @@ struct EvalParams {
                              // already in kernel order (dind_fast_grid_split.cu); 0 = let the dispatcher classify the axes
     int32_t u_is_raw;        // NURBS: u has NOT been pre-multiplied by the weights (only the split grid path accepts that)
     int32_t coherent_points; // neighbouring points share their stencil (cell-sorted plan): prefer narrow, broadcast loads
+    // cell-sorted plan, work items (dind_plan.cu: plan_build_items): item i = plan positions [items[i], items[i + 1]) —
+    // at most item_pts consecutive points of ONE cell, evaluated by one thread that loads every stencil node once
+    const uint32_t* items;
+    int64_t n_items;
+    int32_t item_pts;
     int32_t staged_records;  // out is the plan's staging buffer: component-fastest records of out_point_stride
                              // elements, padded and aligned as plan_record_stride() says (vector stores allowed)
 };
@@ -233,6 +238,14 @@ __device__ __forceinline__ void bspline_basis_rt(const T* __restrict__ Kn, const
     for (int s = 0; s <= p; ++s) w[s] = b[s];   // :97
 }
 
+// Round-to-nearest operations the compiler may NOT contract into FMAs: the same point must get the same bits from
+// every kernel variant that evaluates it (one point or several per thread, derivative order known at compile time or
+// not), which "a * b + c" would leave to each variant's own contraction choices.
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+
 // Compile-time degree version for the specialised kernels: fully unrolled, knots of the
 // 2P+2 wide window are read once.
 template <typename T, int P>
@@ -258,14 +271,16 @@ __device__ __forceinline__ void bspline_basis_ct(const T* __restrict__ Kn, const
             // R_d at i = idx0-P+s and i+1; the lowest slot only needs the second term
             // (b[P-d] is zero on entry), the top slot only the first (b[P+1] == 0).
             T v;
+            // explicit operations (mul_rn / sub_rn / fma): see mul_rn
             if (deriv) {
-                T a = (s > P - d) ? b[s] * Rd[s] : T(0);
-                T c = (s < P) ? b[s + 1] * Rd[s + 1] : T(0);
-                v = T(d) * (a - c);
+                if (s > P - d && s < P) v = mul_rn(T(d), fma(b[s], Rd[s], -mul_rn(b[s + 1], Rd[s + 1])));
+                else if (s > P - d) v = mul_rn(T(d), mul_rn(b[s], Rd[s]));
+                else v = mul_rn(T(d), -mul_rn(b[s + 1], Rd[s + 1]));
             } else {
-                T a = (s > P - d) ? b[s] * ((x - kn[s]) * Rd[s]) : T(0);
-                T c = (s < P) ? b[s + 1] * ((kn[s + d + 1] - x) * Rd[s + 1]) : T(0);
-                v = a + c;
+                if (s > P - d && s < P)
+                    v = fma(b[s], mul_rn(sub_rn(x, kn[s]), Rd[s]), mul_rn(b[s + 1], mul_rn(sub_rn(kn[s + d + 1], x), Rd[s + 1])));
+                else if (s > P - d) v = mul_rn(b[s], mul_rn(sub_rn(x, kn[s]), Rd[s]));
+                else v = mul_rn(b[s + 1], mul_rn(sub_rn(kn[s + d + 1], x), Rd[s + 1]));
             }
             b[s] = v;
         }

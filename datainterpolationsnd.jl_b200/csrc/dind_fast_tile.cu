@@ -1,0 +1,257 @@
+// dind_fast_tile.cu — eval_unstructured! over the cell-sorted plan's WORK ITEMS: one thread evaluates up to PT
+// consecutive plan points that lie in the same cell and loads every stencil node ONCE for all of them.
+//
+// Why: in plan order every lane of a warp reads the same (degree+1)^N stencil, yet with one point per thread
+// every lane still pulls its own copy through the L1 -> register path: BASELINE config 3 (3-D cubic B-spline,
+// 3 components, Float64) moves 64 nodes x 24 B = 1.5 KB per point, 49 KB per warp of points = 384 clk of the
+// 128 B/clk L1 data path against 189 clk of FP64 issue (ncu, profiles/r1_c3_sorted.md: l1tex 94 % busy, FP64
+// pipe 33 %).  The only way to cut L1 -> register bytes per point is to reuse a loaded node in registers, i.e.
+// several points of the SAME cell per thread.  A fixed "PT consecutive points per thread" split straddles cell
+// boundaries (with ~51 points per cell and PT = 4, most warps would contain a straddling thread), so the plan
+// carries a schedule instead (dind_plan.cu: plan_build_items): the plan positions are cut into items of at most
+// PT points that never cross a cell boundary.  A thread takes item i = [items[i], items[i + 1]); slots beyond
+// the item's length repeat its last point and are not stored.
+//
+// The per-point arithmetic (weights, FMA order of the axis-by-axis contraction) is exactly that of
+// unstructured_aos_kernel, so results are bit-identical to the unsorted evaluation.
+//
+// Reference: eval_unstructured! / eval_kernel (src/interpolation_parallel.jl:34-52, :105-138) evaluate one point
+// per work item and redo the whole stencil gather for each.
+#include "dind_kernels.h"
+
+namespace dind {
+
+namespace {
+
+constexpr int TBLOCK = 128;
+
+// same per-dimension stencil as unstructured_aos_kernel (dind_fast_unstructured_aos.cu)
+template <typename T, int W>
+__device__ __forceinline__ void tile_weights(const DimParams<T>& D, T x, int idx, int order, T (&w)[W]) {
+    const int n = D.n_knots;
+    if (W == 2 && D.kind == LINEAR) {
+        const int c = idx - 1;
+        const T t1 = __ldg(D.knots + c), t2 = __ldg(D.knots + c + 1), r = __ldg(D.recip + c);
+        if (order == 0) { w[0] = (t2 - x) * r; w[1] = (x - t1) * r; }
+        else { w[0] = -r; w[1] = r; }
+        return;
+    }
+    bspline_basis_ct<T, W - 1>(D.knots, D.recip, n, idx - 1, x, order, w);
+}
+
+// Axis-by-axis contraction for PT points that share the stencil: node loads are shared, the FMA chains are per point
+// (and per point identical to ContractV of dind_fast_unstructured_aos.cu).
+template <typename T, int D, int W, int C, int PT>
+struct ContractT {
+    static __device__ __forceinline__ void run(const T* __restrict__ p, const T (&w)[PT][MAXN][W], const int (&stride)[MAXN],
+                                               T (&acc)[PT][C]) {
+#pragma unroll
+        for (int q = 0; q < PT; ++q)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[q][c] = T(0);
+#pragma unroll
+        for (int a = 0; a < W; ++a) {
+            T t[PT][C];
+            ContractT<T, D - 1, W, C, PT>::run(p + a * stride[D], w, stride, t);
+#pragma unroll
+            for (int q = 0; q < PT; ++q)
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[q][c] = fma(w[q][D][a], t[q][c], acc[q][c]);
+        }
+    }
+};
+template <typename T, int W, int C, int PT>
+struct ContractT<T, 0, W, C, PT> {
+    static __device__ __forceinline__ void run(const T* __restrict__ p, const T (&w)[PT][MAXN][W], const int (&)[MAXN],
+                                               T (&acc)[PT][C]) {
+        constexpr int S = C == 3 ? 4 : C;
+        Vec<T, C> node[W];
+#pragma unroll
+        for (int a = 0; a < W; ++a) node[a] = load_node<T, C, false>(p + a * S);   // all loads of the row first
+#pragma unroll
+        for (int q = 0; q < PT; ++q)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[q][c] = T(0);
+#pragma unroll
+        for (int a = 0; a < W; ++a)
+#pragma unroll
+            for (int q = 0; q < PT; ++q)
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[q][c] = fma(w[q][0][a], node[a].v[c], acc[q][c]);
+    }
+};
+
+__device__ __forceinline__ void tile_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void tile_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// Inputs are ITEM-MAJOR (dind_plan.cu: plan_item_layout): P.cells[i] is item i's cell word and P.dim[d].t_eval[i * PT + q]
+// the coordinate of its q-th point (padding slots repeat the last point), so every input of a thread is addressed by
+// the thread index alone — one DRAM round trip instead of items -> points — and the inputs of the CTA `pf_ctas`
+// further on can be requested into L2 now.  P.items (item i = plan positions [items[i], items[i + 1])) is only needed
+// for the output position.
+// DER: the derivative orders known at compile time — -1: all zero; d >= 0: order 1 in dimension d, 0 elsewhere (the four
+// evaluations of "value plus first derivatives"); -2: read P.dim[d].order at run time.  With the order a constant the
+// value / derivative branches of every Cox-de Boor stage fold away instead of being predicated (ncu: a third of the
+// FP64 instructions of the basis were predicated off).
+template <typename T, int N, int W, int C, int PT, int MINB, int DER>
+__global__ void __launch_bounds__(TBLOCK, MINB) unstructured_tile_kernel(const __grid_constant__ EvalParams<T> P, int pf_ctas) {
+    const int64_t i = (int64_t)blockIdx.x * TBLOCK + threadIdx.x;
+    if (i >= P.n_items) return;
+    constexpr int S = C == 3 ? 4 : C;
+    const uint32_t cell = __ldcs(P.cells + i);
+    T xs[PT][N];
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+#pragma unroll
+        for (int q = 0; q < PT; ++q) xs[q][d] = __ldcs(P.dim[d].t_eval + i * PT + q);
+    const uint32_t s0 = __ldcs(P.items + i), s1 = __ldcs(P.items + i + 1);
+    {   // L2 prefetch of the same inputs for the CTA pf_ctas ahead (contiguous per warp: a few lines per instruction)
+        const int64_t j = i + (int64_t)pf_ctas * TBLOCK;
+        if (pf_ctas > 0 && j < P.n_items) {
+            tile_prefetch_l2(P.cells + j);
+            tile_prefetch_l2(P.items + j);
+#pragma unroll
+            for (int d = 0; d < N; ++d)
+#pragma unroll
+                for (int q = 0; q < PT; ++q) tile_prefetch_l2(P.dim[d].t_eval + j * PT + q);
+        }
+    }
+    int idx[N];
+    int stride[MAXN];
+    int64_t base = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const DimParams<T>& D = P.dim[d];
+        idx[d] = cell_idx<T>(D, cell);
+        stride[d] = (int)D.u_stride * S;
+        base += (int64_t)(idx[d] - (W == 2 && D.kind == LINEAR ? 1 : W)) * D.u_stride;
+    }
+    const T* ub = P.u_aos + base * S;
+    if constexpr (N == 3 && W == 4) {
+        // the stencil's 16 rows of 4 nodes (128 contiguous bytes each, usually across two lines) into L1 while the
+        // weights are computed: a group of 4 neighbouring lanes (same cell, nearly always) covers all 32 (row, half)
+        const int lane = threadIdx.x & 31;
+        const int half = lane & 1, r0 = ((lane >> 1) & 1) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int r = r0 + j;
+            tile_prefetch_l1(ub + (r & 3) * stride[1] + (r >> 2) * stride[2] + half * 3 * S);
+        }
+    }
+    T w[PT][MAXN][W];
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+#pragma unroll
+        for (int q = 0; q < PT; ++q)
+            tile_weights<T, W>(P.dim[d], xs[q][d], idx[d], DER == -2 ? P.dim[d].order : (DER == d ? 1 : 0), w[q][d]);
+    const int cnt = (int)(s1 - s0);                     // 1..PT points, all in one cell
+    uint32_t ko[PT];
+#pragma unroll
+    for (int q = 0; q < PT; ++q) ko[q] = (P.perm && q < cnt) ? __ldcs(P.perm + s0 + q) : s0 + q;
+    T acc[PT][C];
+    ContractT<T, N - 1, W, C, PT>::run(ub, w, stride, acc);
+#pragma unroll
+    for (int q = 0; q < PT; ++q) {
+        if (q >= cnt) break;
+        if (P.staged_records) {   // one aligned record per point (two-level un-permutation)
+            store_record<T, C>(P.out + (int64_t)ko[q] * P.out_point_stride, acc[q]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) __stcs(P.out + (int64_t)c * P.out_comp_stride + (int64_t)ko[q] * P.out_point_stride, acc[q][c]);
+        }
+    }
+}
+
+// item-major copies of the plan's inputs (see unstructured_tile_kernel)
+template <typename T, int N>
+__global__ void __launch_bounds__(256) plan_item_layout_kernel(const __grid_constant__ EvalParams<T> P, int pts, uint32_t* __restrict__ item_cells,
+                                                               T* const* __restrict__ item_t_unused, T* t0, T* t1, T* t2, T* t3, T* t4, T* t5) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= P.n_items) return;
+    const uint32_t s0 = P.items[i], s1 = P.items[i + 1];
+    const int cnt = (int)(s1 - s0);
+    item_cells[i] = P.cells[s0];
+    T* dst[6] = {t0, t1, t2, t3, t4, t5};
+    for (int q = 0; q < pts; ++q) {
+        const int64_t k = (int64_t)s0 + (q < cnt ? q : cnt - 1);
+#pragma unroll
+        for (int d = 0; d < N; ++d) dst[d][i * pts + q] = __ldcs(P.dim[d].t_eval + k);
+    }
+}
+
+template <typename T, int N, int W, int C, int PT, int MINB>
+cudaError_t launch_tile(const EvalParams<T>& P, cudaStream_t s) {
+    const unsigned nb = (unsigned)((P.n_items + TBLOCK - 1) / TBLOCK);
+    // L2 prefetch distance in CTAs: about twice the CTAs resident on the device (148 SMs x MINB)
+    const int pf = (P.knobs && P.knobs->pf1 >= 0) ? P.knobs->pf1 : 2 * 148 * MINB;
+    int der = -1;
+    for (int d = 0; d < N; ++d) {
+        if (P.dim[d].order == 1 && der == -1) der = d;
+        else if (P.dim[d].order != 0) der = -2;
+    }
+#define DIND_TILE(DD) unstructured_tile_kernel<T, N, W, C, PT, MINB, DD><<<nb, TBLOCK, 0, s>>>(P, pf)
+    if (der == -1) DIND_TILE(-1);
+    else if (der == 0) DIND_TILE(0);
+    else if (der == 1 && N > 1) DIND_TILE((N > 1 ? 1 : -2));
+    else if (der == 2 && N > 2) DIND_TILE((N > 2 ? 2 : -2));
+    else DIND_TILE(-2);
+#undef DIND_TILE
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// Points per item for this configuration (0 = the one-point-per-thread kernels stay in charge).  Worth it where the
+// stencil is large against the per-point inputs: B-spline stencils (W >= 3) of vector-valued u.
+template <typename T>
+int tile_points_per_item(const EvalParams<T>& P, bool gradient) {
+    if (gradient || !P.cells || !aos_supported<T>(P) || P.n_points >= (1LL << 31)) return 0;
+    const int N = P.n_in, W = P.dim[0].width, C = P.n_comp;
+    const int forced = P.knobs ? P.knobs->c3_tile : -1;
+    if (forced == 0) return 0;
+    if (sizeof(T) == 8 && N == 3 && W == 4 && C == 3) return (forced == 2 || forced == 3 || forced == 4) ? forced : 3;
+    return 0;
+}
+
+template <typename T>
+bool try_eval_fast_tile(const EvalParams<T>& P, bool gradient, cudaStream_t s, const char** name, cudaError_t* err, int* launches) {
+    if (!P.items || !P.u_aos || gradient) return false;
+    const int N = P.n_in, W = P.dim[0].width, C = P.n_comp, PT = P.item_pts;
+    *launches = 1;
+    if constexpr (sizeof(T) == 8) {
+        if (N == 3 && W == 4 && C == 3) {
+            if (PT == 2) { *err = launch_tile<T, 3, 4, 3, 2, 4>(P, s); *name = "unstructured_tile<N=3,W=4,C=3,PT=2>"; return true; }
+            if (PT == 3) { *err = launch_tile<T, 3, 4, 3, 3, 3>(P, s); *name = "unstructured_tile<N=3,W=4,C=3,PT=3>"; return true; }
+            if (PT == 4) { *err = launch_tile<T, 3, 4, 3, 4, 2>(P, s); *name = "unstructured_tile<N=3,W=4,C=3,PT=4>"; return true; }
+        }
+    }
+    return false;
+}
+
+// P: plan-order parameters with P.items / P.n_items / P.cells set and dim[d].t_eval = the sorted coordinates
+template <typename T>
+cudaError_t plan_item_layout(const EvalParams<T>& P, int pts, uint32_t* item_cells, T* const* item_t, cudaStream_t s) {
+    const unsigned nb = (unsigned)((P.n_items + 255) / 256);
+    T* t[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int d = 0; d < P.n_in && d < 6; ++d) t[d] = item_t[d];
+    switch (P.n_in) {
+        case 1: plan_item_layout_kernel<T, 1><<<nb, 256, 0, s>>>(P, pts, item_cells, nullptr, t[0], t[1], t[2], t[3], t[4], t[5]); break;
+        case 2: plan_item_layout_kernel<T, 2><<<nb, 256, 0, s>>>(P, pts, item_cells, nullptr, t[0], t[1], t[2], t[3], t[4], t[5]); break;
+        case 3: plan_item_layout_kernel<T, 3><<<nb, 256, 0, s>>>(P, pts, item_cells, nullptr, t[0], t[1], t[2], t[3], t[4], t[5]); break;
+        case 4: plan_item_layout_kernel<T, 4><<<nb, 256, 0, s>>>(P, pts, item_cells, nullptr, t[0], t[1], t[2], t[3], t[4], t[5]); break;
+        case 5: plan_item_layout_kernel<T, 5><<<nb, 256, 0, s>>>(P, pts, item_cells, nullptr, t[0], t[1], t[2], t[3], t[4], t[5]); break;
+        case 6: plan_item_layout_kernel<T, 6><<<nb, 256, 0, s>>>(P, pts, item_cells, nullptr, t[0], t[1], t[2], t[3], t[4], t[5]); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+template cudaError_t plan_item_layout<float>(const EvalParams<float>&, int, uint32_t*, float* const*, cudaStream_t);
+template cudaError_t plan_item_layout<double>(const EvalParams<double>&, int, uint32_t*, double* const*, cudaStream_t);
+
+#define DIND_INST(T)                                                      \
+    template int tile_points_per_item<T>(const EvalParams<T>&, bool);     \
+    template bool try_eval_fast_tile<T>(const EvalParams<T>&, bool, cudaStream_t, const char**, cudaError_t*, int*);
+DIND_INST(float)
+DIND_INST(double)
+
+}  // namespace dind

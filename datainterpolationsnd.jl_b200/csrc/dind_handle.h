@@ -111,6 +111,11 @@ struct dind_interp_s {
     dind::DevBuf plan_perm, plan_stage, plan_scratch, plan_slot2, plan_dest2, plan_cells;
     bool plan_has_cells = false;   // plan_cells holds the packed cell words of the current plan
     bool plan_buckets_valid = false;
+    dind::DevBuf plan_items;       // work items over the plan (tile kernels): n_items + 1 start positions
+    bool plan_items_valid = false;
+    int plan_items_pts = 0;
+    int64_t plan_n_items = 0;
+    dind::DevBuf plan_item_cells, plan_item_t[dind::MAXN];   // item-major copies of the cell words / sorted t_eval
     dind::DevBuf plan_t[dind::MAXN];
     // staging
     dind::DevBuf out_stage[2];            // host `out`: device staging, double buffered for the pipelined (ASYNC) path

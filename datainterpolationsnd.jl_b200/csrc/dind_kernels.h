@@ -28,6 +28,20 @@ template <typename T>
 cudaError_t plan_sort_points(const EvalParams<T>& P, uint32_t* perm, T* const* t_sorted, uint32_t* cells, int cell_bits,
                              void* scratch, size_t* scratch_bytes, cudaStream_t s);
 
+// Work items over the sorted cell words (dind_plan.cu): the plan positions k whose distance from the start of their
+// run of equal cells is a multiple of `pts` — every item is <= pts consecutive points of one cell.  Two calls:
+// items == nullptr counts (n_items_out), then the same call with items (n_items + 1 entries; the last one is n).
+// scratch: n * 4 bytes + CUB temp (scratch_bytes in/out; *scratch = nullptr queries).
+cudaError_t plan_build_items(const uint32_t* cells, int64_t n, int pts, uint32_t* items, int64_t* n_items_out, void* scratch,
+                             size_t* scratch_bytes, cudaStream_t s);
+// Cell-sorted evaluation over work items (dind_fast_tile.cu): one thread = one item.
+template <typename T> int tile_points_per_item(const EvalParams<T>& P, bool gradient);   // 0 = no tile kernel for this configuration
+// item-major copies of the plan's inputs: item_cells[i], item_t[d][i * pts + q] (padding slots repeat the item's last point)
+template <typename T> cudaError_t plan_item_layout(const EvalParams<T>& P, int pts, uint32_t* item_cells, T* const* item_t, cudaStream_t s);
+// P for try_eval_fast_tile: P.cells / P.dim[d].t_eval are the ITEM-MAJOR arrays, P.items the item starts
+template <typename T> bool try_eval_fast_tile(const EvalParams<T>& P, bool gradient, cudaStream_t s, const char** name,
+                                              cudaError_t* err, int* launches);
+
 // Component-fastest repack of u for vector-valued unstructured evaluation (dind_fast_unstructured_aos.cu).
 // elements per node of the component-fastest copy: 3 components are padded to 4 (one aligned vector per node)
 __host__ __device__ inline int aos_node_stride(int n_comp) { return n_comp == 3 ? 4 : n_comp; }

@@ -10,6 +10,13 @@
 // keeps sorted copies of t_eval; the evaluation kernels then run over the sorted list with
 // warp-coherent gathers and scatter each result to its original position.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include <algorithm>
 
 #include "dind_kernels.h"
 
@@ -114,6 +121,70 @@ __global__ void __launch_bounds__(UNB_BLOCK) plan_unbucket_kernel(const T* __res
 }
 
 }  // namespace
+
+// ---- work items: <= pts consecutive points of one cell -----------------------------------------------
+namespace {
+struct RunHead {   // k -> k if a run of equal cell words starts at k, else 0 (max-scan gives every k its run start)
+    const uint32_t* cells;
+    __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return (k == 0 || cells[k] != cells[k - 1]) ? k : 0u; }
+};
+struct IsItem {
+    const uint32_t* run_start;
+    uint32_t pts;
+    __device__ __forceinline__ bool operator()(uint32_t k) const { return (k - run_start[k]) % pts == 0; }
+};
+struct IsItemCount {
+    IsItem f;
+    __device__ __forceinline__ unsigned long long operator()(uint32_t k) const { return f(k) ? 1ull : 0ull; }
+};
+__global__ void items_tail_kernel(uint32_t* items, const unsigned long long* count, uint32_t n) { items[*count] = n; }
+}  // namespace
+
+cudaError_t plan_build_items(const uint32_t* cells, int64_t n, int pts, uint32_t* items, int64_t* n_items_out, void* scratch,
+                             size_t* scratch_bytes, cudaStream_t s) {
+    using Count = cub::CountingInputIterator<uint32_t>;
+    const size_t arr = ((size_t)n * sizeof(uint32_t) + 255) & ~(size_t)255;
+    Count iota(0);
+    cub::TransformInputIterator<uint32_t, RunHead, Count> heads(iota, RunHead{cells});
+    uint32_t* run_start = (uint32_t*)scratch;
+    IsItem pred{run_start, (uint32_t)pts};
+    cub::TransformInputIterator<unsigned long long, IsItemCount, Count> ones(iota, IsItemCount{pred});
+    size_t b_scan = 0, b_red = 0, b_sel = 0;
+    cudaError_t e = cub::DeviceScan::InclusiveScan(nullptr, b_scan, heads, run_start, cub::Max(), (int)n, s);
+    if (e != cudaSuccess) return e;
+    e = cub::DeviceReduce::Sum(nullptr, b_red, ones, (unsigned long long*)nullptr, (int)n, s);
+    if (e != cudaSuccess) return e;
+    e = cub::DeviceSelect::If(nullptr, b_sel, iota, (uint32_t*)nullptr, (unsigned long long*)nullptr, (int)n, pred, s);
+    if (e != cudaSuccess) return e;
+    const size_t cub_bytes = std::max(b_scan, std::max(b_red, b_sel));
+    const size_t need = arr + 256 + cub_bytes;
+    if (!scratch) {
+        *scratch_bytes = need;
+        return cudaSuccess;
+    }
+    if (*scratch_bytes < need) return cudaErrorInvalidValue;
+    unsigned long long* d_count = (unsigned long long*)((char*)scratch + arr);
+    void* cub_tmp = (char*)scratch + arr + 256;
+    size_t tb = cub_bytes;
+    if (!items) {   // pass 1: run starts + number of items
+        e = cub::DeviceScan::InclusiveScan(cub_tmp, tb, heads, run_start, cub::Max(), (int)n, s);
+        if (e != cudaSuccess) return e;
+        tb = cub_bytes;
+        e = cub::DeviceReduce::Sum(cub_tmp, tb, ones, d_count, (int)n, s);
+        if (e != cudaSuccess) return e;
+        unsigned long long c = 0;
+        e = cudaMemcpyAsync(&c, d_count, sizeof c, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(s);
+        *n_items_out = (int64_t)c;
+        return e;
+    }
+    // pass 2 (run_start is still in scratch): the item starts, then the sentinel items[n_items] = n
+    e = cub::DeviceSelect::If(cub_tmp, tb, iota, items, d_count, (int)n, pred, s);
+    if (e != cudaSuccess) return e;
+    items_tail_kernel<<<1, 1, 0, s>>>(items, d_count, (uint32_t)n);
+    return cudaGetLastError();
+}
 
 cudaError_t plan_bucket_schedule(const uint32_t* perm, uint32_t* slot2, uint32_t* dest2, int64_t n, void* scratch,
                                  size_t* scratch_bytes, cudaStream_t s) {
