@@ -162,6 +162,123 @@ __global__ void __launch_bounds__(TBLOCK, MINB) unstructured_tile_kernel(const _
     }
 }
 
+// ---- multilinear tables (BASELINE config 5: 5-D linear, 4 Float32 components) ------------------------------------
+// The one-point-per-thread kernel is issue-bound in plan order (ncu, profiles/r1_c5_sorted.md: issue slots 59 % busy,
+// 645 instructions per point of which 248 are FFMA and ~370 control flow / parameter loads / address arithmetic of
+// the general kernel).  This kernel is specialised for it: Linear dimensions only (no kind / search branches), the
+// item's points share the knot loads, the corner loads and the address arithmetic, and the four components of a
+// node are contracted as two packed pairs — fma.rn.f32x2 (FFMA2), one issue slot for two FMAs.  Packed FMAs round each
+// half exactly like the scalar fmaf of unstructured_aos_kernel and the operation order per point is the same, so the
+// results are bit-identical to the unsorted evaluation.
+template <int D, int PT>
+struct LerpT {
+    static __device__ __forceinline__ void run(const float4* __restrict__ p, const float (&w)[PT][MAXN][2], const int (&stride)[MAXN],
+                                               float2 (&lo)[PT], float2 (&hi)[PT]) {
+        float2 tl[PT], th[PT];
+        LerpT<D - 1, PT>::run(p, w, stride, tl, th);
+#pragma unroll
+        for (int q = 0; q < PT; ++q) {
+            const float2 ww = make_float2(w[q][D][0], w[q][D][0]);
+            lo[q] = __ffma2_rn(ww, tl[q], make_float2(0.f, 0.f));
+            hi[q] = __ffma2_rn(ww, th[q], make_float2(0.f, 0.f));
+        }
+        LerpT<D - 1, PT>::run(p + stride[D], w, stride, tl, th);
+#pragma unroll
+        for (int q = 0; q < PT; ++q) {
+            const float2 ww = make_float2(w[q][D][1], w[q][D][1]);
+            lo[q] = __ffma2_rn(ww, tl[q], lo[q]);
+            hi[q] = __ffma2_rn(ww, th[q], hi[q]);
+        }
+    }
+};
+template <int PT>
+struct LerpT<0, PT> {
+    static __device__ __forceinline__ void run(const float4* __restrict__ p, const float (&w)[PT][MAXN][2], const int (&)[MAXN],
+                                               float2 (&lo)[PT], float2 (&hi)[PT]) {
+        const float4 n0 = __ldg(p), n1 = __ldg(p + 1);
+#pragma unroll
+        for (int q = 0; q < PT; ++q) {
+            const float2 w0 = make_float2(w[q][0][0], w[q][0][0]), w1 = make_float2(w[q][0][1], w[q][0][1]);
+            lo[q] = __ffma2_rn(w1, make_float2(n1.x, n1.y), __ffma2_rn(w0, make_float2(n0.x, n0.y), make_float2(0.f, 0.f)));
+            hi[q] = __ffma2_rn(w1, make_float2(n1.z, n1.w), __ffma2_rn(w0, make_float2(n0.z, n0.w), make_float2(0.f, 0.f)));
+        }
+    }
+};
+
+template <int N, int PT, int MINB, int DER>
+__global__ void __launch_bounds__(TBLOCK, MINB) linear_tile_kernel(const __grid_constant__ EvalParams<float> P, int pf_ctas) {
+    const int64_t i = (int64_t)blockIdx.x * TBLOCK + threadIdx.x;
+    if (i >= P.n_items) return;
+    const uint32_t cell = __ldcs(P.cells + i);
+    float xs[PT][N];
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+#pragma unroll
+        for (int q = 0; q < PT; ++q) xs[q][d] = __ldcs(P.dim[d].t_eval + i * PT + q);
+    const uint32_t s0 = __ldcs(P.items + i), s1 = __ldcs(P.items + i + 1);
+    {
+        const int64_t j = i + (int64_t)pf_ctas * TBLOCK;
+        if (pf_ctas > 0 && j < P.n_items) {
+            tile_prefetch_l2(P.cells + j);
+            tile_prefetch_l2(P.items + j);
+#pragma unroll
+            for (int d = 0; d < N; ++d)
+#pragma unroll
+                for (int q = 0; q < PT; ++q) tile_prefetch_l2(P.dim[d].t_eval + j * PT + q);
+        }
+    }
+    float w[PT][MAXN][2];
+    int stride[MAXN];
+    int64_t base = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const DimParams<float>& D = P.dim[d];
+        const int c = cell_idx<float>(D, cell) - 1;
+        const float t1 = __ldg(D.knots + c), t2 = __ldg(D.knots + c + 1), r = __ldg(D.recip + c);   // once per item
+        const int order = DER == -2 ? D.order : (DER == d ? 1 : 0);
+#pragma unroll
+        for (int q = 0; q < PT; ++q) {
+            if (order == 0) { w[q][d][0] = (t2 - xs[q][d]) * r; w[q][d][1] = (xs[q][d] - t1) * r; }
+            else { w[q][d][0] = -r; w[q][d][1] = r; }
+        }
+        stride[d] = (int)D.u_stride;                 // in nodes = float4 units
+        base += (int64_t)c * D.u_stride;
+    }
+    const int cnt = (int)(s1 - s0);
+    uint32_t ko[PT];
+#pragma unroll
+    for (int q = 0; q < PT; ++q) ko[q] = (P.perm && q < cnt) ? __ldcs(P.perm + s0 + q) : s0 + q;
+    float2 lo[PT], hi[PT];
+    LerpT<N - 1, PT>::run(reinterpret_cast<const float4*>(P.u_aos) + base, w, stride, lo, hi);
+#pragma unroll
+    for (int q = 0; q < PT; ++q) {
+        if (q >= cnt) break;
+        if (P.staged_records) {
+            *reinterpret_cast<float4*>(P.out + (int64_t)ko[q] * P.out_point_stride) = make_float4(lo[q].x, lo[q].y, hi[q].x, hi[q].y);
+        } else {
+            float* o = P.out + (int64_t)ko[q] * P.out_point_stride;
+            __stcs(o, lo[q].x);
+            __stcs(o + P.out_comp_stride, lo[q].y);
+            __stcs(o + 2 * P.out_comp_stride, hi[q].x);
+            __stcs(o + 3 * P.out_comp_stride, hi[q].y);
+        }
+    }
+}
+
+template <int N, int PT, int MINB>
+cudaError_t launch_linear_tile(const EvalParams<float>& P, cudaStream_t s) {
+    const unsigned nb = (unsigned)((P.n_items + TBLOCK - 1) / TBLOCK);
+    const int pf = (P.knobs && P.knobs->pf1 >= 0) ? P.knobs->pf1 : 2 * 148 * MINB;
+    int der = -1;
+    for (int d = 0; d < N; ++d) {
+        if (P.dim[d].order == 1 && der == -1) der = d;
+        else if (P.dim[d].order != 0) der = -2;
+    }
+    if (der == -1) linear_tile_kernel<N, PT, MINB, -1><<<nb, TBLOCK, 0, s>>>(P, pf);
+    else linear_tile_kernel<N, PT, MINB, -2><<<nb, TBLOCK, 0, s>>>(P, pf);
+    return cudaGetLastError();
+}
+
 // item-major copies of the plan's inputs (see unstructured_tile_kernel)
 template <typename T, int N>
 __global__ void __launch_bounds__(256) plan_item_layout_kernel(const __grid_constant__ EvalParams<T> P, int pts, uint32_t* __restrict__ item_cells,
@@ -209,7 +326,20 @@ int tile_points_per_item(const EvalParams<T>& P, bool gradient) {
     const int N = P.n_in, W = P.dim[0].width, C = P.n_comp;
     const int forced = P.knobs ? P.knobs->c3_tile : -1;
     if (forced == 0) return 0;
-    if (sizeof(T) == 8 && N == 3 && W == 4 && C == 3) return (forced == 2 || forced == 3 || forced == 4) ? forced : 3;
+    if (sizeof(T) == 8 && N == 3 && W == 4 && C == 3) return (forced == 2 || forced == 3 || forced == 4) ? forced : (forced == 32 ? 3 : (forced == 22 ? 2 : 3));
+    if (sizeof(T) == 4 && N == 5 && W == 2 && C == 4) {
+        bool linear = true;
+        double cells_total = 1.0;
+        for (int d = 0; d < N; ++d) {
+            linear = linear && P.dim[d].kind == LINEAR;
+            cells_total *= (double)(P.dim[d].n_u - 1);
+        }
+        if (!linear) return 0;
+        if (forced == 2 || forced == 4) return forced;
+        // expected points per cell for points spread over the table: few -> 2 per item, many -> 4; hardly any -> none
+        const double density = (double)P.n_points / cells_total;
+        return density >= 8.0 ? 4 : (density >= 1.0 ? 2 : 0);
+    }
     return 0;
 }
 
@@ -218,8 +348,17 @@ bool try_eval_fast_tile(const EvalParams<T>& P, bool gradient, cudaStream_t s, c
     if (!P.items || !P.u_aos || gradient) return false;
     const int N = P.n_in, W = P.dim[0].width, C = P.n_comp, PT = P.item_pts;
     *launches = 1;
+    if constexpr (sizeof(T) == 4) {
+        if (N == 5 && W == 2 && C == 4) {
+            if (PT == 2) { *err = launch_linear_tile<5, 2, 5>(P, s); *name = "linear_tile<N=5,C=4,PT=2,ffma2>"; return true; }
+            if (PT == 4) { *err = launch_linear_tile<5, 4, 3>(P, s); *name = "linear_tile<N=5,C=4,PT=4,ffma2>"; return true; }
+        }
+    }
     if constexpr (sizeof(T) == 8) {
         if (N == 3 && W == 4 && C == 3) {
+            const int forced = P.knobs ? P.knobs->c3_tile : -1;
+            if (forced == 32) { *err = launch_tile<T, 3, 4, 3, 3, 4>(P, s); *name = "unstructured_tile<N=3,W=4,C=3,PT=3,4cta>"; return true; }
+            if (forced == 22) { *err = launch_tile<T, 3, 4, 3, 2, 5>(P, s); *name = "unstructured_tile<N=3,W=4,C=3,PT=2,5cta>"; return true; }
             if (PT == 2) { *err = launch_tile<T, 3, 4, 3, 2, 4>(P, s); *name = "unstructured_tile<N=3,W=4,C=3,PT=2>"; return true; }
             if (PT == 3) { *err = launch_tile<T, 3, 4, 3, 3, 3>(P, s); *name = "unstructured_tile<N=3,W=4,C=3,PT=3>"; return true; }
             if (PT == 4) { *err = launch_tile<T, 3, 4, 3, 4, 2>(P, s); *name = "unstructured_tile<N=3,W=4,C=3,PT=4>"; return true; }
