@@ -780,9 +780,9 @@ def make_workload(args):
     if args.workload == "c1":
         return C1()
     if args.workload == "c3":
-        return C3(100_000_000 if args.full else 20_000_000)
+        return C3(args.points or (100_000_000 if args.full else 20_000_000))
     if args.workload == "c5":
-        return C5(4_000_000_000 if args.full else 100_000_000)
+        return C5(args.points or (4_000_000_000 if args.full else 100_000_000))
     raise SystemExit(f"unknown workload {args.workload}")
 
 
@@ -794,6 +794,7 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--impl", default="dind")
     ap.add_argument("--full", action="store_true", help="full-size point counts for c3 / c5")
+    ap.add_argument("--points", type=int, default=0, help="c3 / c5: points per GPU (overrides --full)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink c2 (debugging only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only-headline", action="store_true", help="skip the other BASELINE configs (`configs` / `point_sharded`)")

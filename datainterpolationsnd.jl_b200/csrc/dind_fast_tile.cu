@@ -81,6 +81,26 @@ struct ContractT<T, 0, W, C, PT> {
     }
 };
 
+// Loads the compiler must issue where they are written (volatile asm keeps its place among the other volatile
+// statements): left alone, ptxas sinks the knot / output-slot loads to their first use to save registers, and every
+// one of them then costs a full dependent round trip (ncu source view of linear_tile_kernel: 13 % of all stall
+// samples on the first FADD of the last dimension's weights, 5 % on the store address).
+__device__ __forceinline__ float ld_pinned(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_pinned(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_pinned(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ void tile_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tile_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -209,13 +229,13 @@ template <int N, int PT, int MINB, int DER>
 __global__ void __launch_bounds__(TBLOCK, MINB) linear_tile_kernel(const __grid_constant__ EvalParams<float> P, int pf_ctas) {
     const int64_t i = (int64_t)blockIdx.x * TBLOCK + threadIdx.x;
     if (i >= P.n_items) return;
-    const uint32_t cell = __ldcs(P.cells + i);
+    const uint32_t cell = ld_pinned(P.cells + i);
     float xs[PT][N];
 #pragma unroll
     for (int d = 0; d < N; ++d)
 #pragma unroll
-        for (int q = 0; q < PT; ++q) xs[q][d] = __ldcs(P.dim[d].t_eval + i * PT + q);
-    const uint32_t s0 = __ldcs(P.items + i), s1 = __ldcs(P.items + i + 1);
+        for (int q = 0; q < PT; ++q) xs[q][d] = ld_pinned(P.dim[d].t_eval + i * PT + q);
+    const uint32_t s0 = ld_pinned(P.items + i), s1 = ld_pinned(P.items + i + 1);
     {
         const int64_t j = i + (int64_t)pf_ctas * TBLOCK;
         if (pf_ctas > 0 && j < P.n_items) {
@@ -232,24 +252,39 @@ __global__ void __launch_bounds__(TBLOCK, MINB) linear_tile_kernel(const __grid_
     int64_t base = 0;
 #pragma unroll
     for (int d = 0; d < N; ++d) {
+        stride[d] = (int)P.dim[d].u_stride;                 // in nodes = float4 units
+        base += (int64_t)(cell_idx<float>(P.dim[d], cell) - 1) * P.dim[d].u_stride;
+    }
+    const float4* ub = reinterpret_cast<const float4*>(P.u_aos) + base;
+    float kt1[N], kt2[N], kr[N];   // knots and reciprocal span of the item's cell: once per item, all requested now
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const int c = cell_idx<float>(P.dim[d], cell) - 1;
+        kt1[d] = ld_pinned(P.dim[d].knots + c);
+        kt2[d] = ld_pinned(P.dim[d].knots + c + 1);
+        kr[d] = ld_pinned(P.dim[d].recip + c);
+    }
+    const int cnt = (int)(s1 - s0);
+    uint32_t ko[PT];
+#pragma unroll
+    for (int q = 0; q < PT; ++q) ko[q] = s0 + q;
+    if (P.perm) {
+#pragma unroll
+        for (int q = 0; q < PT; ++q) ko[q] = ld_pinned(P.perm + s0 + (q < cnt ? q : cnt - 1));
+    }
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
         const DimParams<float>& D = P.dim[d];
-        const int c = cell_idx<float>(D, cell) - 1;
-        const float t1 = __ldg(D.knots + c), t2 = __ldg(D.knots + c + 1), r = __ldg(D.recip + c);   // once per item
+        const float t1 = kt1[d], t2 = kt2[d], r = kr[d];
         const int order = DER == -2 ? D.order : (DER == d ? 1 : 0);
 #pragma unroll
         for (int q = 0; q < PT; ++q) {
             if (order == 0) { w[q][d][0] = (t2 - xs[q][d]) * r; w[q][d][1] = (xs[q][d] - t1) * r; }
             else { w[q][d][0] = -r; w[q][d][1] = r; }
         }
-        stride[d] = (int)D.u_stride;                 // in nodes = float4 units
-        base += (int64_t)c * D.u_stride;
     }
-    const int cnt = (int)(s1 - s0);
-    uint32_t ko[PT];
-#pragma unroll
-    for (int q = 0; q < PT; ++q) ko[q] = (P.perm && q < cnt) ? __ldcs(P.perm + s0 + q) : s0 + q;
     float2 lo[PT], hi[PT];
-    LerpT<N - 1, PT>::run(reinterpret_cast<const float4*>(P.u_aos) + base, w, stride, lo, hi);
+    LerpT<N - 1, PT>::run(ub, w, stride, lo, hi);
 #pragma unroll
     for (int q = 0; q < PT; ++q) {
         if (q >= cnt) break;
@@ -336,9 +371,11 @@ int tile_points_per_item(const EvalParams<T>& P, bool gradient) {
         }
         if (!linear) return 0;
         if (forced == 2 || forced == 4) return forced;
-        // expected points per cell for points spread over the table: few -> 2 per item, many -> 4; hardly any -> none
+        // expected points per cell for points spread over the table: hardly any -> no items (one point per thread).
+        // 2 points per item at 8 CTAs/SM beats 4 per item (166 registers, 3 CTAs/SM) at every density measured:
+        // 1e8 points (3.5 per cell) 57.0 vs 43.9 Gpoints/s, 5e8 points (17 per cell) 66.6 vs 54.0 (63.6 at 4 CTAs/SM)
         const double density = (double)P.n_points / cells_total;
-        return density >= 8.0 ? 4 : (density >= 1.0 ? 2 : 0);
+        return density >= 1.0 ? 2 : 0;
     }
     return 0;
 }
@@ -350,7 +387,15 @@ bool try_eval_fast_tile(const EvalParams<T>& P, bool gradient, cudaStream_t s, c
     *launches = 1;
     if constexpr (sizeof(T) == 4) {
         if (N == 5 && W == 2 && C == 4) {
-            if (PT == 2) { *err = launch_linear_tile<5, 2, 5>(P, s); *name = "linear_tile<N=5,C=4,PT=2,ffma2>"; return true; }
+            const int forced = P.knobs ? P.knobs->chunk : 0;   // experiment: DIND_CHUNK=6|8 -> CTAs per SM
+            if (PT == 2 && forced == 6) { *err = launch_linear_tile<5, 2, 6>(P, s); *name = "linear_tile<N=5,C=4,PT=2,ffma2,6cta>"; return true; }
+            if (PT == 2 && forced == 8) { *err = launch_linear_tile<5, 2, 8>(P, s); *name = "linear_tile<N=5,C=4,PT=2,ffma2,8cta>"; return true; }
+            if (PT == 2 && forced == 5) { *err = launch_linear_tile<5, 2, 5>(P, s); *name = "linear_tile<N=5,C=4,PT=2,ffma2,5cta>"; return true; }
+            // 8 CTAs/SM (64 registers, no spills): the kernel waits on gathers, resident warps are what hides them
+            // (plan order, 1e8 points: 5 CTAs 52.4, 6 CTAs 53.6, 8 CTAs 57.0 Gpoints/s)
+            if (PT == 2) { *err = launch_linear_tile<5, 2, 8>(P, s); *name = "linear_tile<N=5,C=4,PT=2,ffma2>"; return true; }
+            if (PT == 4 && forced == 4) { *err = launch_linear_tile<5, 4, 4>(P, s); *name = "linear_tile<N=5,C=4,PT=4,ffma2,4cta>"; return true; }
+            if (PT == 4 && forced == 5) { *err = launch_linear_tile<5, 4, 5>(P, s); *name = "linear_tile<N=5,C=4,PT=4,ffma2,5cta>"; return true; }
             if (PT == 4) { *err = launch_linear_tile<5, 4, 3>(P, s); *name = "linear_tile<N=5,C=4,PT=4,ffma2>"; return true; }
         }
     }
