@@ -61,7 +61,7 @@ Knobs read_knobs() {
     k.no_aos = getenv("DIND_NO_AOS") != nullptr;
     k.no_small = getenv("DIND_NO_SMALL") != nullptr;
     k.no_slice = getenv("DIND_NO_SLICE") != nullptr;
-    k.no_persist = getenv("DIND_NO_PERSIST") != nullptr;
+    k.persist = getenv("DIND_PERSIST") != nullptr;
     return k;
 }
 
@@ -387,7 +387,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
             CUDA_TRY(plan_sort_points<T>(P, (uint32_t*)h->plan_perm.p, ts, cells, cell_bits, h->plan_scratch.p, &scratch_bytes, h->stream));
             h->launches += 2 + N;
             h->plan_valid = true;
-            h->plan_items_valid = false;
+            h->plan_items[0].valid = h->plan_items[1].valid = false;
             h->plan_buckets_valid = false;
             h->plan_n = n_points;
         }
@@ -445,34 +445,36 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         P.u_aos = (const T*)h->u_aos.p;
     }
     // cell-sorted plan: the work-item schedule of the tile kernels (<= pts consecutive points of one cell per thread)
+    dind_interp_s::PlanItems* IT = nullptr;
     if (use_aos && P.cells) {
         const int pts = tile_points_per_item<T>(P, gradient);
         if (pts > 0) {
-            if (!h->plan_items_valid || h->plan_items_pts != pts) {
+            IT = &h->plan_items[gradient ? 1 : 0];
+            if (!IT->valid || IT->pts != pts) {
                 size_t sb = 0;
                 CUDA_TRY(plan_build_items(nullptr, n_points, pts, nullptr, nullptr, nullptr, &sb, h->stream));
                 CUDA_TRY(h->plan_scratch.ensure(sb));
                 sb = h->plan_scratch.cap;
                 int64_t n_items = 0;
                 CUDA_TRY(plan_build_items(P.cells, n_points, pts, nullptr, &n_items, h->plan_scratch.p, &sb, h->stream));
-                CUDA_TRY(h->plan_items.ensure((size_t)(n_items + 1) * sizeof(uint32_t)));
-                CUDA_TRY(plan_build_items(P.cells, n_points, pts, (uint32_t*)h->plan_items.p, &n_items, h->plan_scratch.p, &sb, h->stream));
-                h->plan_n_items = n_items;
-                h->plan_items_pts = pts;
-                P.items = (const uint32_t*)h->plan_items.p;
+                CUDA_TRY(IT->items.ensure((size_t)(n_items + 1) * sizeof(uint32_t)));
+                CUDA_TRY(plan_build_items(P.cells, n_points, pts, (uint32_t*)IT->items.p, &n_items, h->plan_scratch.p, &sb, h->stream));
+                IT->n = n_items;
+                IT->pts = pts;
+                P.items = (const uint32_t*)IT->items.p;
                 P.n_items = n_items;
-                CUDA_TRY(h->plan_item_cells.ensure((size_t)n_items * sizeof(uint32_t)));
+                CUDA_TRY(IT->cells.ensure((size_t)n_items * sizeof(uint32_t)));
                 T* it[MAXN];
                 for (int d = 0; d < N; ++d) {
-                    CUDA_TRY(h->plan_item_t[d].ensure((size_t)n_items * pts * sizeof(T)));
-                    it[d] = (T*)h->plan_item_t[d].p;
+                    CUDA_TRY(IT->t[d].ensure((size_t)n_items * pts * sizeof(T)));
+                    it[d] = (T*)IT->t[d].p;
                 }
-                CUDA_TRY(plan_item_layout<T>(P, pts, (uint32_t*)h->plan_item_cells.p, it, h->stream));
-                h->plan_items_valid = true;
+                CUDA_TRY(plan_item_layout<T>(P, pts, (uint32_t*)IT->cells.p, it, h->stream));
+                IT->valid = true;
                 h->launches += 5;
             }
-            P.items = (const uint32_t*)h->plan_items.p;
-            P.n_items = h->plan_n_items;
+            P.items = (const uint32_t*)IT->items.p;
+            P.n_items = IT->n;
             P.item_pts = pts;
         }
     }
@@ -488,7 +490,13 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     if (gradient) {
         // one fused pass when the configuration is in the kernel's envelope, otherwise n_in + 1
         // ordinary evaluations into the n_in + 1 output slots
-        if (fast_ok) handled = try_eval_fast_gradient<T>(P, h->stream, &name, &err, &nlaunch);
+        if (fast_ok && IT) {
+            EvalParams<T> Q = P;   // the tile kernels read the item-major copies of the plan's inputs
+            Q.cells = (const uint32_t*)IT->cells.p;
+            for (int d = 0; d < N; ++d) Q.dim[d].t_eval = (const T*)IT->t[d].p;
+            handled = try_eval_fast_tile<T>(Q, true, h->stream, &name, &err, &nlaunch);
+        }
+        if (fast_ok && !handled) handled = try_eval_fast_gradient<T>(P, h->stream, &name, &err, &nlaunch);
         if (!handled) {
             const int64_t slot = P.out_comp_stride * h->n_comp;   // n_points * n_comp, or n_comp when staged in plan order
             for (int sidx = 0; sidx <= N && err == cudaSuccess; ++sidx) {
@@ -504,11 +512,11 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
             handled = true;
         }
     }
-    if (use_aos && !handled && P.items) {
+    if (use_aos && !handled && IT) {
         EvalParams<T> Q = P;   // the tile kernels read the item-major copies of the plan's inputs
-        Q.cells = (const uint32_t*)h->plan_item_cells.p;
-        for (int d = 0; d < N; ++d) Q.dim[d].t_eval = (const T*)h->plan_item_t[d].p;
-        handled = try_eval_fast_tile<T>(Q, gradient, h->stream, &name, &err, &nlaunch);
+        Q.cells = (const uint32_t*)IT->cells.p;
+        for (int d = 0; d < N; ++d) Q.dim[d].t_eval = (const T*)IT->t[d].p;
+        handled = try_eval_fast_tile<T>(Q, false, h->stream, &name, &err, &nlaunch);
     }
     if (use_aos && !handled) handled = try_eval_fast_unstructured_aos<T>(P, h->stream, &name, &err, &nlaunch);
     if (split && !handled) {
@@ -678,8 +686,7 @@ int dind_destroy(dind_handle_t h) {
     if (h->ev_kernel) cudaEventDestroy(h->ev_kernel);
     for (int i = 0; i < 2; ++i) if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
     comm_release(h);
-    h->plan_perm.release(); h->plan_stage.release(); h->plan_scratch.release(); h->plan_slot2.release(); h->plan_dest2.release(); h->plan_cells.release(); h->plan_items.release(); h->plan_item_cells.release();
-    for (int d = 0; d < MAXN; ++d) h->plan_item_t[d].release();
+    h->plan_perm.release(); h->plan_stage.release(); h->plan_scratch.release(); h->plan_slot2.release(); h->plan_dest2.release(); h->plan_cells.release(); h->plan_items[0].release(); h->plan_items[1].release();
     for (int d = 0; d < MAXN; ++d) h->plan_t[d].release();
     delete h;
     return DIND_OK;

@@ -146,7 +146,7 @@ struct Knobs {
     int l2_warm = -1;    // DIND_L2_WARM: bulk L2 warm-up of u (-1 = default)
     int c3_tile = -1;    // DIND_C3_TILE: points per thread of the cell-sorted cubic kernel (-1 = default)
     bool no_lut = false, no_split = false, no_cells = false, no_aos = false, no_small = false, no_slice = false;
-    bool no_persist = false;   // DIND_NO_PERSIST: two launches instead of the persistent two-stage grid kernel
+    bool persist = false;      // DIND_PERSIST=1: the persistent two-stage 4-D grid kernel instead of two launches
 };
 
 template <typename T>

@@ -16,6 +16,7 @@
 // FMAs per output drop from ~30 to ~6 (x2 for NURBS) and nothing is gathered; the price is one
 // round trip of T through HBM/L2 (config 4: 2 x 537 MB written and read once).
 #include <algorithm>
+#include <cstring>
 
 #include "dind_kernels.h"
 
@@ -54,7 +55,15 @@ __global__ void iota_kernel(int32_t* p, int n) {
 // One plane of the window: rows of T for the thread's 2 x VB outputs, contracted along axis 3 into window
 // slot PH.  The slot is a template parameter so that the window never moves between registers: the walk
 // switches (warp-uniformly) on the slot and rotates the three or four axis-4 WEIGHTS instead.
-template <typename T, int W, int W4, bool NURBS, int REL, int PH>
+// CO: T is being produced by other CTAs of the SAME launch (fused kernel below): read it with ordinary loads, not
+// through the non-coherent path.
+template <typename T, bool CO>
+__device__ __forceinline__ T ld_t(const T* p) {
+    if constexpr (CO) return *p;
+    else return __ldg(p);
+}
+
+template <typename T, int W, int W4, bool NURBS, int REL, int PH, bool CO = false>
 __device__ __forceinline__ void batch_plane(const T* const (&bn)[SB_VB], int64_t pl, int64_t dd, int64_t stepB, int64_t rel_b,
                                             int64_t pf_off, bool pf_ok, const T (&w3)[2][W], T (&wn)[W4][2][SB_VB],
                                             T (&wd)[NURBS ? W4 : 1][2][SB_VB]) {
@@ -66,8 +75,8 @@ __device__ __forceinline__ void batch_plane(const T* const (&bn)[SB_VB], int64_t
         const T* q = bn[v] + pl;
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
-            rn[v][r] = __ldg(q);
-            if (NURBS) rd[v][r] = __ldg(q + dd);
+            rn[v][r] = ld_t<T, CO>(q);
+            if (NURBS) rd[v][r] = ld_t<T, CO>(q + dd);
             // the walk is sequential along axis 4: ask for the same rows of the next plane now
             if (pf_ok) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(q + pf_off));
@@ -94,7 +103,7 @@ __device__ __forceinline__ void batch_plane(const T* const (&bn)[SB_VB], int64_t
 
 // REL = 0 / 1: the two g_3 rows of the thread start at the same node / one node apart and share
 // their W + REL rows of T; REL = 2: unrelated rows (down-sampling, unsorted t_eval), loaded separately.
-template <typename T, int W, int W4, bool NURBS, int REL>
+template <typename T, int W, int W4, bool NURBS, int REL, bool CO = false>
 __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s_i0, const T* s_w, int g_lo, int g_n,
                                            const int64_t (&boff)[SB_VB], const bool (&okb)[SB_VB], int g3a, bool ok1,
                                            int i3a, int i3b, const T (&w3)[2][W]) {
@@ -135,15 +144,15 @@ __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s
                 const int pidx = i4 + (W4 - shift) + s;
                 const bool pf_ok = pidx + SB_PF < Q.n4;
                 const int64_t pl = Bn3 * (int64_t)pidx;
-                if (W4 == 1 || phase == 0) batch_plane<T, W, W4, NURBS, REL, 0>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
+                if (W4 == 1 || phase == 0) batch_plane<T, W, W4, NURBS, REL, 0, CO>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
                 if constexpr (W4 > 1) {
-                    if (phase == 1) batch_plane<T, W, W4, NURBS, REL, 1>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
+                    if (phase == 1) batch_plane<T, W, W4, NURBS, REL, 1, CO>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
                 }
                 if constexpr (W4 > 2) {
-                    if (phase == 2) batch_plane<T, W, W4, NURBS, REL, 2>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
+                    if (phase == 2) batch_plane<T, W, W4, NURBS, REL, 2, CO>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
                 }
                 if constexpr (W4 > 3) {
-                    if (phase == 3) batch_plane<T, W, W4, NURBS, REL, 3>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
+                    if (phase == 3) batch_plane<T, W, W4, NURBS, REL, 3, CO>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
                 }
                 phase = phase + 1 == W4 ? 0 : phase + 1;
             }
@@ -193,20 +202,20 @@ __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s
     }
 }
 
-template <typename T, int W, int W4, bool NURBS>
-__global__ void __launch_bounds__(SB_BLOCK, 4) grid_batch_kernel(const __grid_constant__ BatchParams<T> Q) {
-    __shared__ int s_i0[SB_MAXCHUNK];
-    __shared__ T s_w[SB_MAXCHUNK * W4];
-    const int g_lo = blockIdx.y * Q.chunk;
+// One CTA's share of stage 2: block (bx, by) of NT threads; bseg0 = first batch segment of the B-tile this block
+// works in (0 for the stand-alone kernel).  s_i0 / s_w: shared-memory staging of the axis-4 table slice.
+template <typename T, int W, int W4, bool NURBS, int NT, bool CO>
+__device__ __forceinline__ void batch_body(const BatchParams<T>& Q, int bx, int by, int bseg0, int* s_i0, T* s_w) {
+    const int g_lo = by * Q.chunk;
     const int g_n = min(Q.g4 - g_lo, Q.chunk);
-    for (int i = threadIdx.x; i < g_n; i += SB_BLOCK) s_i0[i] = __ldg(Q.i0_4 + g_lo + i);
-    for (int i = threadIdx.x; i < g_n * W4; i += SB_BLOCK) s_w[i] = __ldg(Q.w_4 + (int64_t)g_lo * W4 + i);
+    for (int i = threadIdx.x; i < g_n; i += NT) s_i0[i] = __ldg(Q.i0_4 + g_lo + i);
+    for (int i = threadIdx.x; i < g_n * W4; i += NT) s_w[i] = __ldg(Q.w_4 + (int64_t)g_lo * W4 + i);
     __syncthreads();
-    const int item = blockIdx.x * SB_WARPS + (threadIdx.x >> 5);
+    const int item = bx * (NT / 32) + (threadIdx.x >> 5);
     if (item >= Q.n_items) return;
     const int lane = threadIdx.x & 31;
     const int g3p = item / Q.n_bseg;
-    const int bseg = item - g3p * Q.n_bseg;
+    const int bseg = bseg0 + item - g3p * Q.n_bseg;
     int64_t boff[SB_VB];
     bool okb[SB_VB];
 #pragma unroll
@@ -226,9 +235,16 @@ __global__ void __launch_bounds__(SB_BLOCK, 4) grid_batch_kernel(const __grid_co
         w3[1][a] = __ldg(Q.w_3 + g3b * W + a);
     }
     const int rel = i3b - i3a;
-    if (rel == 0) batch_walk<T, W, W4, NURBS, 0>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
-    else if (rel == 1) batch_walk<T, W, W4, NURBS, 1>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
-    else batch_walk<T, W, W4, NURBS, 2>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
+    if (rel == 0) batch_walk<T, W, W4, NURBS, 0, CO>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
+    else if (rel == 1) batch_walk<T, W, W4, NURBS, 1, CO>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
+    else batch_walk<T, W, W4, NURBS, 2, CO>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
+}
+
+template <typename T, int W, int W4, bool NURBS>
+__global__ void __launch_bounds__(SB_BLOCK, 4) grid_batch_kernel(const __grid_constant__ BatchParams<T> Q) {
+    __shared__ int s_i0[SB_MAXCHUNK];
+    __shared__ T s_w[SB_MAXCHUNK * W4];
+    batch_body<T, W, W4, NURBS, SB_BLOCK, false>(Q, blockIdx.x, blockIdx.y, 0, s_i0, s_w);
 }
 
 // ---- stage 1 with the (n_1, n_2) slice of u in shared memory ----------------------------------------
@@ -254,12 +270,11 @@ struct SliceParams {
     const T* w_2;
 };
 
+// One slice (i_3, i_4) of stage 1, outputs g_2 in chunks [ch_lo, ch_hi) of S1_CHUNK (the whole axis for the
+// stand-alone kernel; one B-tile for the fused kernel).
 template <typename T, int W, int NARR>
-__global__ void __launch_bounds__(S1_BLOCK) grid_slice_kernel(const __grid_constant__ SliceParams<T> Q) {
-    extern __shared__ __align__(16) unsigned char s1_smem[];
-    T* S = reinterpret_cast<T*>(s1_smem);   // [NARR][n1 * n2]
+__device__ __forceinline__ void slice_body(const SliceParams<T>& Q, int64_t sl, int ch_lo, int ch_hi, T* S) {
     const int nn = Q.n1 * Q.n2;
-    const int64_t sl = blockIdx.x;
     {
         const T* src0 = Q.a0 + sl * Q.slice_stride;
         const T* srcw = (NARR == 2 ? Q.a1 : Q.premul) + sl * Q.slice_stride;
@@ -291,12 +306,11 @@ __global__ void __launch_bounds__(S1_BLOCK) grid_slice_kernel(const __grid_const
         }
     }
     __syncthreads();
-    const int n_chunks = (Q.g2 + S1_CHUNK - 1) / S1_CHUNK;
-    const int n_tasks = Q.g1 * n_chunks;
+    const int n_tasks = Q.g1 * (ch_hi - ch_lo);
     const int64_t out_slice = (int64_t)Q.g1 * Q.g2;
     for (int task = threadIdx.x; task < n_tasks; task += S1_BLOCK) {
-        const int ch = task / Q.g1;
-        const int g1 = task - ch * Q.g1;
+        const int ch = ch_lo + task / Q.g1;
+        const int g1 = task - (ch - ch_lo) * Q.g1;
         const int i1 = __ldg(Q.i0_1 + g1);
         T w1[W];
 #pragma unroll
@@ -355,6 +369,102 @@ __global__ void __launch_bounds__(S1_BLOCK) grid_slice_kernel(const __grid_const
     }
 }
 
+template <typename T, int W, int NARR>
+__global__ void __launch_bounds__(S1_BLOCK) grid_slice_kernel(const __grid_constant__ SliceParams<T> Q) {
+    extern __shared__ __align__(16) unsigned char s1_smem[];
+    slice_body<T, W, NARR>(Q, blockIdx.x, 0, (Q.g2 + S1_CHUNK - 1) / S1_CHUNK, reinterpret_cast<T*>(s1_smem));
+}
+
+// ---- both stages in ONE persistent launch -----------------------------------------------------------------
+// Run as two kernels, T (config 4: 2 x 537 MB) is written to HBM by stage 1 and read back by stage 2: 2.1 GB of the
+// 4.7 GB the evaluation moves, for 2.4 GB algorithmic.  Alternating the two kernels over L2-sized tiles lost to the
+// per-launch ramp-up and tail.  Here one grid of resident CTAs drains two ordered task queues:
+//   stage-2 tasks (B-tile h, chunk c of the last axis, block bx) — the product;
+//   stage-1 tasks (B-tile h, slice (i_3, i_4)), in plane order i_4 — the supply.
+// A CTA takes the next stage-2 task, looks up the planes i_4 its chunk needs and, while one of them is incomplete,
+// executes stage-1 tasks itself (demand-driven: the supply runs just ahead of the consumers); once the stage-1 queue
+// is empty it waits.  Every incomplete plane it may wait for was claimed earlier by a CTA that is running, and
+// stage-1 tasks never wait, so there is no deadlock for any t_eval order.  With the stage-2 chunk a few outputs long
+// and B cut into tiles, the live part of T is a handful of planes (tens of MB) that stay in the 126 MB L2 between
+// the store of stage 1 and the loads of stage 2.
+// MEASURED (B200, config 4, 128^4 outputs): 1.64 ms with 8-output chunks and two B-tiles, 1.38 ms with 16, 1.25 ms
+// with 32, 1.17 ms with 32 and no B-tiling — against 1.01 ms for the two separate launches.  Short chunks pay the
+// window start-up of the axis-4 walk (6 planes contracted for 8 outputs instead of 4) and per-task scheduling; long
+// chunks leave more of T live than L2 holds.  The two-launch path therefore stays the default and this kernel is
+// opt-in (DIND_PERSIST=1, parity-tested); making it win needs stage-1 tasks that stage only the rows of u a thin
+// B-tile touches, so that the walk can stay long while the live part of T stays small.
+// Completion is published per (tile, plane) with a device-scope
+// counter (store T; __syncthreads; __threadfence + atomicAdd by one thread) and consumed by a volatile load +
+// __threadfence + __syncthreads; T is then read with ordinary (coherent) loads.
+template <typename T>
+struct FusedParams {
+    SliceParams<T> S;
+    BatchParams<T> Q;        // Q.chunk / Q.n_bseg / Q.n_items are per B-tile
+    int n_slices, n3;        // slices per tile, slices per plane
+    int n_bt, ch_per_tile;   // B-tiles (ranges of g_2) and stage-1 chunks of g_2 per tile
+    int n_chunks4, bx_per;   // stage-2 tasks = n_bt x n_chunks4 x bx_per
+    int* ctrl;               // [0] stage-1 queue head, [1] stage-2 queue head, [2 + h * n4 + i_4] finished slices of (tile, plane)
+};
+
+constexpr size_t FUSED_CTRL_BYTES = 64 << 10;   // queue heads + per (tile, plane) completion counters, at the end of the scratch
+constexpr int FU_BLOCK = S1_BLOCK;   // 256 threads: 8 stage-2 items per task
+constexpr int FU_MAXCHUNK = 32;
+
+template <typename T, int W, bool NURBS>
+__global__ void __launch_bounds__(FU_BLOCK, 2) grid_split_fused_kernel(const __grid_constant__ FusedParams<T> F) {
+    extern __shared__ __align__(16) unsigned char s1_smem[];
+    T* S = reinterpret_cast<T*>(s1_smem);
+    __shared__ int s_i0[FU_MAXCHUNK];
+    __shared__ T s_w[FU_MAXCHUNK * W];
+    __shared__ int s_task, s_s1, s_ready;
+    const int n4 = F.Q.n4;
+    const int n_tasks2 = F.n_bt * F.n_chunks4 * F.bx_per, n_tasks1 = F.n_bt * F.n_slices;
+    volatile int* done = F.ctrl + 2;
+    for (;;) {
+        if (threadIdx.x == 0) s_task = atomicAdd(F.ctrl + 1, 1);
+        __syncthreads();
+        const int t2 = s_task;
+        if (t2 >= n_tasks2) break;
+        const int h = t2 / (F.n_chunks4 * F.bx_per);
+        const int r = t2 - h * (F.n_chunks4 * F.bx_per);
+        const int c = r / F.bx_per, bx = r - c * F.bx_per;
+        for (;;) {
+            if (threadIdx.x < 32) {
+                // planes the chunk needs: [min, max + W) of its first nodes; lane l looks at output l and at plane l
+                const int g_lo = c * F.Q.chunk, g_hi = min(F.Q.g4, g_lo + F.Q.chunk);
+                const int lane = threadIdx.x;
+                const int p0 = __ldg(F.Q.i0_4 + min(g_lo + lane, g_hi - 1));
+                const int p_lo = __reduce_min_sync(0xffffffffu, p0), p_hi = __reduce_max_sync(0xffffffffu, p0) + W;
+                int ready = 1;
+                for (int p = p_lo + lane; p < p_hi; p += 32) ready = ready && done[h * n4 + p] >= F.n3;
+                ready = __all_sync(0xffffffffu, ready);
+                if (lane == 0) {
+                    s_ready = ready;
+                    s_s1 = ready ? -1 : atomicAdd(F.ctrl, 1);
+                    if (ready) __threadfence();
+                }
+            }
+            __syncthreads();
+            if (s_ready) break;
+            const int s1 = s_s1;
+            if (s1 < n_tasks1) {
+                const int h1 = s1 / F.n_slices, sl = s1 - h1 * F.n_slices;
+                slice_body<T, W, NURBS ? 2 : 1>(F.S, sl, h1 * F.ch_per_tile, (h1 + 1) * F.ch_per_tile, S);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    __threadfence();
+                    atomicAdd(F.ctrl + 2 + h1 * n4 + sl / F.n3, 1);
+                }
+            } else {
+                __nanosleep(256);
+            }
+            __syncthreads();
+        }
+        batch_body<T, W, W, NURBS, FU_BLOCK, true>(F.Q, bx, c, h * F.Q.n_bseg, s_i0, s_w);
+        __syncthreads();
+    }
+}
+
 template <typename T, int W>
 cudaError_t launch_slice(const SliceParams<T>& Q, int64_t n_slices, cudaStream_t s) {
     const int narr = Q.a1 ? 2 : 1;
@@ -384,6 +494,40 @@ cudaError_t launch_batch(const BatchParams<T>& Q0, cudaStream_t s) {
     if (Q.td) grid_batch_kernel<T, W, W4, true><<<grid, SB_BLOCK, 0, s>>>(Q);
     else grid_batch_kernel<T, W, W4, false><<<grid, SB_BLOCK, 0, s>>>(Q);
     return cudaGetLastError();
+}
+
+// tiles / sizes of the fused launch; false = not applicable (then the two kernels run one after the other)
+template <typename T>
+bool fused_plan(const EvalParams<T>& P, FusedParams<T>& F, size_t ctrl_ints_cap) {
+    const int W = P.dim[0].width;
+    if (!(P.knobs && P.knobs->persist)) return false;   // opt-in (DIND_PERSIST=1): measured slower than the two launches, see above
+    if (P.n_comp != 1 || P.dim[2].width != W || P.dim[3].width != W || !grid_split_slice_ok<T>(P)) return false;
+    const int64_t g1 = P.dim[0].n_eval, g2 = P.dim[1].n_eval;
+    const int n3 = P.dim[2].n_u, n4 = P.dim[3].n_u;
+    const int narr = P.wts ? 2 : 1;
+    // B-tiles: ranges of g_2 (whole stage-1 chunks) so that a plane of T of one tile is at most ~10 MB
+    const int n_ch2 = (int)((g2 + S1_CHUNK - 1) / S1_CHUNK);
+    if (g2 % S1_CHUNK != 0) return false;
+    int n_bt = 1;
+    while (n_bt < n_ch2 && n_ch2 % (n_bt * 2) == 0 &&
+           (double)g1 * (g2 / n_bt) * n3 * sizeof(T) * narr > ((P.knobs && P.knobs->pf1 > 0) ? P.knobs->pf1 * 1.0e6 : 10.0e6)) n_bt *= 2;
+    const int64_t b_tile = g1 * (g2 / n_bt);
+    if (b_tile % (32 * SB_VB) != 0) return false;
+    if ((size_t)(2 + n_bt * n4) > ctrl_ints_cap) return false;
+    F.n_slices = n3 * n4;
+    F.n3 = n3;
+    F.n_bt = n_bt;
+    F.ch_per_tile = n_ch2 / n_bt;
+    // stage-2 chunk along the last axis: short, so that few planes of T are live (experiment knob DIND_CHUNK)
+    int chunk = (P.knobs && P.knobs->chunk > 0) ? P.knobs->chunk : 8;
+    chunk = std::max(1, std::min(chunk, FU_MAXCHUNK));
+    F.Q.chunk = chunk;
+    F.n_chunks4 = (int)((P.dim[3].n_eval + chunk - 1) / chunk);
+    F.Q.n_bseg = (int)(b_tile / (32 * SB_VB));
+    const int64_t items = (int64_t)F.Q.n_bseg * ((P.dim[2].n_eval + 1) / 2);
+    F.Q.n_items = (int)items;
+    F.bx_per = (int)((items + FU_BLOCK / 32 - 1) / (FU_BLOCK / 32));
+    return (int64_t)n_bt * F.n_chunks4 * F.bx_per < (1LL << 30);
 }
 
 }  // namespace
@@ -420,7 +564,7 @@ size_t grid_split_scratch_bytes(const EvalParams<T>& P) {
     const size_t t_elems = (size_t)P.dim[0].n_eval * P.dim[1].n_eval * P.dim[2].n_u * P.dim[3].n_u;
     const size_t t_bytes = (t_elems * sizeof(T) + 255) & ~size_t(255);
     const size_t iota = ((size_t)std::max(P.dim[2].n_u, P.dim[3].n_u) * sizeof(int32_t) + 255) & ~size_t(255);
-    return iota + t_bytes * (P.wts ? 2 : 1);
+    return iota + t_bytes * (P.wts ? 2 : 1) + FUSED_CTRL_BYTES;
 }
 
 template <typename T>
@@ -471,6 +615,46 @@ cudaError_t launch_grid_split(const EvalParams<T>& P, void* scratch, cudaStream_
     S1.slice_stride = (int64_t)n1 * n2;
     S1.i0_1 = P.dim[0].tab_i0; S1.w_1 = P.dim[0].tab_w;
     S1.i0_2 = P.dim[1].tab_i0; S1.w_2 = P.dim[1].tab_w;
+    // both stages in one persistent launch (scalar u, all four axes B-splines, slices fit shared memory)
+    {
+        FusedParams<T> F;
+        memset(&F, 0, sizeof F);
+        F.S = S1;
+        F.S.a0 = P.u;
+        F.S.t0 = tn;
+        F.S.a1 = td ? P.wts : nullptr;
+        F.S.premul = P.u_is_raw ? P.wts : nullptr;
+        F.S.t1 = td;
+        F.Q.tn = tn; F.Q.td = td; F.Q.out = P.out; F.Q.B = B; F.Q.n3 = n3; F.Q.n4 = n4;
+        F.Q.g3 = (int)P.dim[2].n_eval; F.Q.g4 = (int)P.dim[3].n_eval;
+        F.Q.i0_3 = P.dim[2].tab_i0; F.Q.w_3 = P.dim[2].tab_w; F.Q.i0_4 = P.dim[3].tab_i0; F.Q.w_4 = P.dim[3].tab_w;
+        F.ctrl = (int*)((char*)scratch + iota_bytes + t_bytes * (td ? 2 : 1));
+        if (fused_plan<T>(P, F, FUSED_CTRL_BYTES / sizeof(int))) {
+            const size_t ctrl_bytes = (size_t)(2 + F.n_bt * n4) * sizeof(int);
+            if ((e = cudaMemsetAsync(F.ctrl, 0, ctrl_bytes, s)) != cudaSuccess) return e;
+            const size_t smem = (size_t)(td ? 2 : 1) * n1 * n2 * sizeof(T);
+            int dev = 0, n_sm = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            const int n_tasks2 = F.n_bt * F.n_chunks4 * F.bx_per;
+            const int grid = std::min(n_tasks2, 2 * n_sm);
+#define DIND_FUSED(WW, NU)                                                                                                  \
+    {                                                                                                                      \
+        if ((e = cudaFuncSetAttribute(grid_split_fused_kernel<T, WW, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                      (int)smem)) != cudaSuccess) return e;                                                \
+        grid_split_fused_kernel<T, WW, NU><<<grid, FU_BLOCK, smem, s>>>(F);                                                 \
+    }
+            if (W == 3 && td) DIND_FUSED(3, true)
+            else if (W == 3) DIND_FUSED(3, false)
+            else if (td) DIND_FUSED(4, true)
+            else DIND_FUSED(4, false)
+#undef DIND_FUSED
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            *launches += 1;
+            *name = W == 3 ? "grid_split_fused<N=2+2,W=3>" : "grid_split_fused<N=2+2,W=4>";
+            return cudaSuccess;
+        }
+    }
     bool den_done = false;
     if (td && !use_slice) {
         P1.u = P.wts;

@@ -182,6 +182,126 @@ __global__ void __launch_bounds__(TBLOCK, MINB) unstructured_tile_kernel(const _
     }
 }
 
+// ---- fused value + first partials over work items (dind_eval_unstructured_gradient) -----------------------------
+// Same contraction as ContractGV of dind_fast_gradient.cu (per point the same FMAs in the same order: bit-identical
+// results), node loads shared by the item's PT points.
+template <typename T, int D, int W, int C, int PT>
+struct ContractGT {
+    static __device__ __forceinline__ void run(const T* __restrict__ p, const T (&w)[PT][MAXN][W], const T (&dw)[PT][MAXN][W],
+                                               const int (&stride)[MAXN], T (&r)[PT][(D + 2) * C]) {
+#pragma unroll
+        for (int q = 0; q < PT; ++q)
+#pragma unroll
+            for (int j = 0; j < (D + 2) * C; ++j) r[q][j] = T(0);
+#pragma unroll
+        for (int a = 0; a < W; ++a) {
+            T sub[PT][(D + 1) * C];
+            ContractGT<T, D - 1, W, C, PT>::run(p + a * stride[D], w, dw, stride, sub);
+#pragma unroll
+            for (int q = 0; q < PT; ++q) {
+#pragma unroll
+                for (int j = 0; j < (D + 1) * C; ++j) r[q][j] = fma(w[q][D][a], sub[q][j], r[q][j]);
+#pragma unroll
+                for (int c = 0; c < C; ++c) r[q][(D + 1) * C + c] = fma(dw[q][D][a], sub[q][c], r[q][(D + 1) * C + c]);
+            }
+        }
+    }
+};
+template <typename T, int W, int C, int PT>
+struct ContractGT<T, 0, W, C, PT> {
+    static __device__ __forceinline__ void run(const T* __restrict__ p, const T (&w)[PT][MAXN][W], const T (&dw)[PT][MAXN][W],
+                                               const int (&)[MAXN], T (&r)[PT][2 * C]) {
+        constexpr int S = C == 3 ? 4 : C;
+        Vec<T, C> node[W];
+#pragma unroll
+        for (int a = 0; a < W; ++a) node[a] = load_node<T, C, false>(p + a * S);
+#pragma unroll
+        for (int q = 0; q < PT; ++q)
+#pragma unroll
+            for (int j = 0; j < 2 * C; ++j) r[q][j] = T(0);
+#pragma unroll
+        for (int a = 0; a < W; ++a)
+#pragma unroll
+            for (int q = 0; q < PT; ++q)
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    r[q][c] = fma(w[q][0][a], node[a].v[c], r[q][c]);
+                    r[q][C + c] = fma(dw[q][0][a], node[a].v[c], r[q][C + c]);
+                }
+    }
+};
+
+template <typename T, int N, int W, int C, int PT, int MINB>
+__global__ void __launch_bounds__(TBLOCK, MINB) gradient_tile_kernel(const __grid_constant__ EvalParams<T> P, int pf_ctas) {
+    const int64_t i = (int64_t)blockIdx.x * TBLOCK + threadIdx.x;
+    if (i >= P.n_items) return;
+    constexpr int S = C == 3 ? 4 : C;
+    const uint32_t cell = __ldcs(P.cells + i);
+    T xs[PT][N];
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+#pragma unroll
+        for (int q = 0; q < PT; ++q) xs[q][d] = __ldcs(P.dim[d].t_eval + i * PT + q);
+    const uint32_t s0 = __ldcs(P.items + i), s1 = __ldcs(P.items + i + 1);
+    {
+        const int64_t j = i + (int64_t)pf_ctas * TBLOCK;
+        if (pf_ctas > 0 && j < P.n_items) {
+            tile_prefetch_l2(P.cells + j);
+            tile_prefetch_l2(P.items + j);
+#pragma unroll
+            for (int d = 0; d < N; ++d)
+#pragma unroll
+                for (int q = 0; q < PT; ++q) tile_prefetch_l2(P.dim[d].t_eval + j * PT + q);
+        }
+    }
+    int idx[N];
+    int stride[MAXN];
+    int64_t base = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const DimParams<T>& D = P.dim[d];
+        idx[d] = cell_idx<T>(D, cell);
+        stride[d] = (int)D.u_stride * S;
+        base += (int64_t)(idx[d] - (W == 2 && D.kind == LINEAR ? 1 : W)) * D.u_stride;
+    }
+    T w[PT][MAXN][W], dw[PT][MAXN][W];
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+#pragma unroll
+        for (int q = 0; q < PT; ++q) {
+            tile_weights<T, W>(P.dim[d], xs[q][d], idx[d], 0, w[q][d]);
+            tile_weights<T, W>(P.dim[d], xs[q][d], idx[d], 1, dw[q][d]);
+        }
+    const int cnt = (int)(s1 - s0);
+    uint32_t ko[PT];
+#pragma unroll
+    for (int q = 0; q < PT; ++q) ko[q] = (P.perm && q < cnt) ? __ldcs(P.perm + s0 + q) : s0 + q;
+    T g[PT][(N + 1) * C];
+    ContractGT<T, N - 1, W, C, PT>::run(P.u_aos + base * S, w, dw, stride, g);
+    const int64_t slot = P.out_comp_stride * C;
+#pragma unroll
+    for (int q = 0; q < PT; ++q) {
+        if (q >= cnt) break;
+        T* o = P.out + (int64_t)ko[q] * P.out_point_stride;
+        if (P.staged_records) {
+            store_record<T, (N + 1) * C>(o, g[q]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < N + 1; ++j)
+#pragma unroll
+                for (int c = 0; c < C; ++c) __stcs(o + (int64_t)c * P.out_comp_stride + j * slot, g[q][j * C + c]);
+        }
+    }
+}
+
+template <typename T, int N, int W, int C, int PT, int MINB>
+cudaError_t launch_gradient_tile(const EvalParams<T>& P, cudaStream_t s) {
+    const unsigned nb = (unsigned)((P.n_items + TBLOCK - 1) / TBLOCK);
+    const int pf = (P.knobs && P.knobs->pf1 >= 0) ? P.knobs->pf1 : 2 * 148 * MINB;
+    gradient_tile_kernel<T, N, W, C, PT, MINB><<<nb, TBLOCK, 0, s>>>(P, pf);
+    return cudaGetLastError();
+}
+
 // ---- multilinear tables (BASELINE config 5: 5-D linear, 4 Float32 components) ------------------------------------
 // The one-point-per-thread kernel is issue-bound in plan order (ncu, profiles/r1_c5_sorted.md: issue slots 59 % busy,
 // 645 instructions per point of which 248 are FFMA and ~370 control flow / parameter loads / address arithmetic of
@@ -357,10 +477,11 @@ cudaError_t launch_tile(const EvalParams<T>& P, cudaStream_t s) {
 // stencil is large against the per-point inputs: B-spline stencils (W >= 3) of vector-valued u.
 template <typename T>
 int tile_points_per_item(const EvalParams<T>& P, bool gradient) {
-    if (gradient || !P.cells || !aos_supported<T>(P) || P.n_points >= (1LL << 31)) return 0;
+    if (!P.cells || !aos_supported<T>(P) || P.n_points >= (1LL << 31)) return 0;
     const int N = P.n_in, W = P.dim[0].width, C = P.n_comp;
     const int forced = P.knobs ? P.knobs->c3_tile : -1;
     if (forced == 0) return 0;
+    if (gradient) return (sizeof(T) == 8 && N == 3 && W == 4 && C == 3) ? 2 : 0;   // 12 accumulators per point: two points per item
     if (sizeof(T) == 8 && N == 3 && W == 4 && C == 3) return (forced == 2 || forced == 3 || forced == 4) ? forced : (forced == 32 ? 3 : (forced == 22 ? 2 : 3));
     if (sizeof(T) == 4 && N == 5 && W == 2 && C == 4) {
         bool linear = true;
@@ -382,9 +503,19 @@ int tile_points_per_item(const EvalParams<T>& P, bool gradient) {
 
 template <typename T>
 bool try_eval_fast_tile(const EvalParams<T>& P, bool gradient, cudaStream_t s, const char** name, cudaError_t* err, int* launches) {
-    if (!P.items || !P.u_aos || gradient) return false;
+    if (!P.items || !P.u_aos) return false;
     const int N = P.n_in, W = P.dim[0].width, C = P.n_comp, PT = P.item_pts;
     *launches = 1;
+    if (gradient) {
+        if constexpr (sizeof(T) == 8) {
+            if (N == 3 && W == 4 && C == 3 && PT == 2) {
+                *err = launch_gradient_tile<T, 3, 4, 3, 2, 2>(P, s);
+                *name = "unstructured_gradient_tile<N=3,W=4,C=3,PT=2>";
+                return true;
+            }
+        }
+        return false;
+    }
     if constexpr (sizeof(T) == 4) {
         if (N == 5 && W == 2 && C == 4) {
             const int forced = P.knobs ? P.knobs->chunk : 0;   // experiment: DIND_CHUNK=6|8 -> CTAs per SM

@@ -111,11 +111,20 @@ struct dind_interp_s {
     dind::DevBuf plan_perm, plan_stage, plan_scratch, plan_slot2, plan_dest2, plan_cells;
     bool plan_has_cells = false;   // plan_cells holds the packed cell words of the current plan
     bool plan_buckets_valid = false;
-    dind::DevBuf plan_items;       // work items over the plan (tile kernels): n_items + 1 start positions
-    bool plan_items_valid = false;
-    int plan_items_pts = 0;
-    int64_t plan_n_items = 0;
-    dind::DevBuf plan_item_cells, plan_item_t[dind::MAXN];   // item-major copies of the cell words / sorted t_eval
+    // work items over the plan (tile kernels), one set for evaluations [0] and one for fused gradients [1] (they cut
+    // the plan into items of different lengths): n_items + 1 start positions, item-major copies of the cell words and
+    // of the sorted t_eval
+    struct PlanItems {
+        dind::DevBuf items, cells, t[dind::MAXN];
+        bool valid = false;
+        int pts = 0;
+        int64_t n = 0;
+        void release() {
+            items.release(); cells.release();
+            for (int d = 0; d < dind::MAXN; ++d) t[d].release();
+            valid = false;
+        }
+    } plan_items[2];
     dind::DevBuf plan_t[dind::MAXN];
     // staging
     dind::DevBuf out_stage[2];            // host `out`: device staging, double buffered for the pipelined (ASYNC) path

@@ -200,6 +200,38 @@ def test_c4_nurbs_grid_properties(D, torch):
     itp.close()
 
 
+def test_c4_persistent_two_stage_kernel_matches_two_launches(D, torch, monkeypatch):
+    """DIND_PERSIST=1 runs both separable stages of the 4-D grid evaluation in one persistent launch (stage-2 CTAs
+    produce the stage-1 planes they wait for; dind_fast_grid_split.cu).  Opt-in because it measured slower than the
+    two launches; same numbers up to the summation order of the window, any t_eval order along the last axis."""
+    rng = np.random.default_rng(44)
+    ts = [knots(rng, 31, np.float64) for _ in range(4)]
+    shape = (32,) * 4
+    gen = torch.Generator(device="cuda").manual_seed(19)
+    u = D.f_empty(shape, np.float64, "cuda"); u.copy_(torch.rand(shape, generator=gen, device="cuda", dtype=torch.float64))
+    w = D.f_empty(shape, np.float64, "cuda"); w.copy_(torch.rand(shape, generator=gen, device="cuda", dtype=torch.float64) + 0.5)
+    for sort_last in (True, False):
+        xs = [np.sort(rng.uniform(t[0], t[-1], n)) for t, n in zip(ts, (64, 64, 40, 50))]
+        if not sort_last:
+            rng.shuffle(xs[3])
+        for cache in (None, D.NURBSWeights(w)):
+            outs = []
+            for persist in (False, True):
+                if persist:
+                    monkeypatch.setenv("DIND_PERSIST", "1")
+                else:
+                    monkeypatch.delenv("DIND_PERSIST", raising=False)
+                dims = tuple(D.BSplineInterpolationDimension(t, 2, t_eval=torch.from_numpy(x).cuda()) for t, x in zip(ts, xs))
+                itp = D.NDInterpolation(u, dims, cache=cache)
+                outs.append(D.eval_grid(itp))
+                assert itp.last_kernel.startswith("grid_split_fused" if persist else "grid_split<"), itp.last_kernel
+                itp.close()
+            # the last-axis walk sums its window in slot order, and the slot <-> plane rotation depends on where a
+            # chunk starts (8-output chunks here, 32 in the two-launch path): equal up to the summation order
+            assert float((outs[0] - outs[1]).abs().max()) <= 1e-14 * float(outs[0].abs().max())
+    monkeypatch.delenv("DIND_PERSIST", raising=False)
+
+
 # ---- config 5: 5-D linear lookup table u (32^5, 4) Float32, point-sharded ------------------------------------
 def _c5_setup(D, torch, seed=5):
     rng = np.random.default_rng(seed)
