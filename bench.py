@@ -340,17 +340,50 @@ def run_gpu(args, wl, rank, world, local_rank):
     for i in range(1, args.warmup):
         step(i)
     barrier()
+    # A 0.1 ms step is launch-bound from Python (set_u + eval_grid! are two ctypes calls, ~0.1 ms per step when several
+    # ranks share the host): the steps of one rotation over the u buffers are captured once in a CUDA graph — the API
+    # calls are capturable (no allocation, no synchronisation with DIND_FLAG_ASYNC and device arrays) — and the timed
+    # region replays it.  Steps that do not fill a graph run eagerly; --no-graph times the eager loop.
+    graph, per_graph, launch_mode = None, 0, "eager (one set_u + eval call per step from Python)"
     l0 = itp.launch_count
+    step(args.warmup)
+    launches_per_step = itp.launch_count - l0
+    if wl.grid and not args.no_graph and not (args.gather and world > 1):
+        try:
+            per_graph = len(u_bufs)
+            cap_stream = torch.cuda.Stream(device=dev)
+            cap_stream.wait_stream(stream)
+            itp.set_stream(cap_stream.cuda_stream)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=cap_stream):
+                for i in range(per_graph):
+                    step(i)
+            graph = g
+            launch_mode = f"cuda graph of {per_graph} steps (one per u buffer), replayed; remainder eager"
+        except Exception as exc:   # noqa: BLE001 — capture is an optimisation of the measurement, not of the product
+            graph, launch_mode = None, f"eager (graph capture failed: {type(exc).__name__})"
+        finally:
+            itp.set_stream(stream.cuda_stream)
+        torch.cuda.synchronize()
+        if graph is not None:
+            graph.replay()   # warm
+            torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     with ClockSampler(local_rank) as clocks:
         ev0.record(stream)
-        for i in range(args.steps):
+        done = 0
+        if graph is not None:
+            for _ in range(args.steps // per_graph):
+                graph.replay()
+            done = (args.steps // per_graph) * per_graph
+        for i in range(done, args.steps):
             step(args.warmup + i)
         ev1.record(stream)
         barrier()
     ms_total = ev0.elapsed_time(ev1)
     ms_per_step_rank = ms_total / args.steps
-    launches = itp.launch_count - l0
+    launches = launches_per_step * args.steps
     kernel = itp.last_kernel
 
     # ---- cache construction as its own timed path: new t_eval (borrowed device pointers) ->
@@ -453,7 +486,7 @@ def run_gpu(args, wl, rank, world, local_rank):
                                    f"owns sweep r — every rank evaluates exactly the N = 1 problem (same u extent, density and algorithmic bytes)"
                                    if wl.grid and world > 1 else "")),
                    "l2": f"working set exceeds L2 (126 MB): output streamed, u rotates over {wl.n_u_buffers} buffers" if wl.grid else "t_eval + out exceed L2",
-                   "kernel": kernel, "first_call_ms_incl_cache_build": round(first_call_ms, 3), "cache_build": cache_build, "gradient": args.gradient, "all_gather_outputs": bool(args.gather and world > 1), "point_order": ("iid random, evaluated through the cell-sorted plan" + (", output left in plan order" if args.plan_order else "") if args.sorted else "iid random") if not wl.grid else "grid"},
+                   "kernel": kernel, "launch": launch_mode, "first_call_ms_incl_cache_build": round(first_call_ms, 3), "cache_build": cache_build, "gradient": args.gradient, "all_gather_outputs": bool(args.gather and world > 1), "point_order": ("iid random, evaluated through the cell-sorted plan" + (", output left in plan order" if args.plan_order else "") if args.sorted else "iid random") if not wl.grid else "grid"},
         "e2e": {"value": round(pts_step_all / (e2e_ms * 1e-3) / 1e9, 4), "unit": "Gpoints/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "host (pinned) buffers through the public API, H2D + kernel + D2H every step; grid workloads queue the steps (DIND_FLAG_ASYNC) so D2H(i) overlaps H2D(i+1)",
@@ -797,6 +830,7 @@ def main():
     ap.add_argument("--points", type=int, default=0, help="c3 / c5: points per GPU (overrides --full)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink c2 (debugging only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="grid headline: time the eager Python loop instead of CUDA-graph replays")
     ap.add_argument("--only-headline", action="store_true", help="skip the other BASELINE configs (`configs` / `point_sharded`)")
     ap.add_argument("--no-cache-build", action="store_true", help="skip the separate timing of cache construction")
     ap.add_argument("--gradient", choices=["fused", "separate"], default=None,
