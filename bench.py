@@ -429,6 +429,11 @@ def run_gpu(args, wl, rank, world, local_rank):
         out_host2 = torch.empty(wl.n_grid[::-1], dtype=tdt).pin_memory()
         outs_np = [out_np, out_host2.numpy().transpose(*rev)]
         n_e2e = max(4, min(args.steps, 10))
+        for i in range(2):                                  # untimed: the pipelined path's one-time set-up (copy stream,
+            itp_h.set_u(u_np[i % 2], flags=1)               # events, second 537 MB staging buffer) — with 8 ranks on one
+            D.eval_grid_(outs_np[i % 2], itp_h, flags=1)    # host these cost ~0.3 s and were inside the timed region
+        itp_h.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for i in range(n_e2e):
             itp_h.set_u(u_np[i % 2], flags=1)               # H2D of this step's u
