@@ -308,7 +308,11 @@ class NDInterpolation:
     def set_u(self, u, flags=0):
         """Swap in a new `u` of the same shape (re-evaluation with the t_eval caches kept).
         flags=1 (DIND_FLAG_ASYNC) with a pinned host array: the upload is only queued — keep `u`
-        unchanged until `synchronize()`."""
+        unchanged until `synchronize()`.
+
+        A CUDA tensor is BORROWED (zero-copy), and the library keeps copies derived from it (the
+        component-fastest `u` of vector-valued fields, `u * weights` for NURBS): after changing a device
+        `u` (or the weights) IN PLACE, call `set_u` again before evaluating."""
         a = _Arr(u, self.dtype)
         if len(a.shape) - self.N_in != self.N_out:
             raise DindError(_lib.ERR_SIZE_MISMATCH, "u changed its number of dimensions")
