@@ -204,16 +204,23 @@ __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s
 
 // One CTA's share of stage 2: block (bx, by) of NT threads; bseg0 = first batch segment of the B-tile this block
 // works in (0 for the stand-alone kernel).  s_i0 / s_w: shared-memory staging of the axis-4 table slice.
+// NT threads cooperate: a CTA (tid = threadIdx.x) or, in the fused kernel, ONE warp (NT = 32, tid = lane)
+template <int NT>
+__device__ __forceinline__ void group_sync() {
+    if constexpr (NT == 32) __syncwarp();
+    else __syncthreads();
+}
+
 template <typename T, int W, int W4, bool NURBS, int NT, bool CO>
-__device__ __forceinline__ void batch_body(const BatchParams<T>& Q, int bx, int by, int bseg0, int* s_i0, T* s_w) {
+__device__ __forceinline__ void batch_body(const BatchParams<T>& Q, int bx, int by, int bseg0, int* s_i0, T* s_w, int tid) {
     const int g_lo = by * Q.chunk;
     const int g_n = min(Q.g4 - g_lo, Q.chunk);
-    for (int i = threadIdx.x; i < g_n; i += NT) s_i0[i] = __ldg(Q.i0_4 + g_lo + i);
-    for (int i = threadIdx.x; i < g_n * W4; i += NT) s_w[i] = __ldg(Q.w_4 + (int64_t)g_lo * W4 + i);
-    __syncthreads();
-    const int item = bx * (NT / 32) + (threadIdx.x >> 5);
+    for (int i = tid; i < g_n; i += NT) s_i0[i] = __ldg(Q.i0_4 + g_lo + i);
+    for (int i = tid; i < g_n * W4; i += NT) s_w[i] = __ldg(Q.w_4 + (int64_t)g_lo * W4 + i);
+    group_sync<NT>();
+    const int item = bx * (NT / 32) + (tid >> 5);
     if (item >= Q.n_items) return;
-    const int lane = threadIdx.x & 31;
+    const int lane = tid & 31;
     const int g3p = item / Q.n_bseg;
     const int bseg = bseg0 + item - g3p * Q.n_bseg;
     int64_t boff[SB_VB];
@@ -244,7 +251,7 @@ template <typename T, int W, int W4, bool NURBS>
 __global__ void __launch_bounds__(SB_BLOCK, 4) grid_batch_kernel(const __grid_constant__ BatchParams<T> Q) {
     __shared__ int s_i0[SB_MAXCHUNK];
     __shared__ T s_w[SB_MAXCHUNK * W4];
-    batch_body<T, W, W4, NURBS, SB_BLOCK, false>(Q, blockIdx.x, blockIdx.y, 0, s_i0, s_w);
+    batch_body<T, W, W4, NURBS, SB_BLOCK, false>(Q, blockIdx.x, blockIdx.y, 0, s_i0, s_w, threadIdx.x);
 }
 
 // ---- stage 1 with the (n_1, n_2) slice of u in shared memory ----------------------------------------
@@ -270,47 +277,50 @@ struct SliceParams {
     const T* w_2;
 };
 
-// One slice (i_3, i_4) of stage 1, outputs g_2 in chunks [ch_lo, ch_hi) of S1_CHUNK (the whole axis for the
-// stand-alone kernel; one B-tile for the fused kernel).
-template <typename T, int W, int NARR>
-__device__ __forceinline__ void slice_body(const SliceParams<T>& Q, int64_t sl, int ch_lo, int ch_hi, T* S) {
-    const int nn = Q.n1 * Q.n2;
+// One slice (i_3, i_4) of stage 1: outputs g_2 in [g2_lo, g2_hi), `sub` consecutive outputs per thread, from the
+// rows [r_lo, r_lo + r_n) of the slice staged in shared memory (the whole slice and axis for the stand-alone kernel;
+// one thin B-tile and only the rows it touches for the fused kernel).
+template <typename T, int W, int NARR, int NT>
+__device__ __forceinline__ void slice_body(const SliceParams<T>& Q, int64_t sl, int g2_lo, int g2_hi, int sub, int r_lo, int r_n, T* S,
+                                           int tid) {
+    const int nn = Q.n1 * r_n;
     {
-        const T* src0 = Q.a0 + sl * Q.slice_stride;
-        const T* srcw = (NARR == 2 ? Q.a1 : Q.premul) + sl * Q.slice_stride;
+        const T* src0 = Q.a0 + sl * Q.slice_stride + (int64_t)r_lo * Q.n1;
+        const T* srcw = (NARR == 2 ? Q.a1 : Q.premul) + sl * Q.slice_stride + (int64_t)r_lo * Q.n1;
         if (NARR == 2 || Q.premul) {
             // NURBS numerator u*w (src/interpolation_methods.jl:124-131) formed here instead of by a separate pass
             // four elements per thread and step, all eight loads issued before the first shared-memory store
             constexpr int U = 4;
-            int i = threadIdx.x;
-            for (; i + (U - 1) * S1_BLOCK < nn; i += U * S1_BLOCK) {
+            int i = tid;
+            for (; i + (U - 1) * NT < nn; i += U * NT) {
                 T uv[U], wv[U];
 #pragma unroll
                 for (int q = 0; q < U; ++q) {
-                    wv[q] = __ldg(srcw + i + q * S1_BLOCK);
-                    uv[q] = __ldcs(src0 + i + q * S1_BLOCK);
+                    wv[q] = __ldg(srcw + i + q * NT);
+                    uv[q] = __ldcs(src0 + i + q * NT);
                 }
 #pragma unroll
                 for (int q = 0; q < U; ++q) {
-                    S[i + q * S1_BLOCK] = Q.premul ? uv[q] * wv[q] : uv[q];
-                    if (NARR == 2) S[nn + i + q * S1_BLOCK] = wv[q];
+                    S[i + q * NT] = Q.premul ? uv[q] * wv[q] : uv[q];
+                    if (NARR == 2) S[nn + i + q * NT] = wv[q];
                 }
             }
-            for (; i < nn; i += S1_BLOCK) {
+            for (; i < nn; i += NT) {
                 const T wv = __ldg(srcw + i);
                 S[i] = Q.premul ? __ldcs(src0 + i) * wv : __ldcs(src0 + i);
                 if (NARR == 2) S[nn + i] = wv;
             }
         } else {
-            for (int i = threadIdx.x; i < nn; i += S1_BLOCK) S[i] = __ldcs(src0 + i);
+            for (int i = tid; i < nn; i += NT) S[i] = __ldcs(src0 + i);
         }
     }
-    __syncthreads();
-    const int n_tasks = Q.g1 * (ch_hi - ch_lo);
+    group_sync<NT>();
+    const int n_sub = (g2_hi - g2_lo + sub - 1) / sub;
+    const int n_tasks = Q.g1 * n_sub;
     const int64_t out_slice = (int64_t)Q.g1 * Q.g2;
-    for (int task = threadIdx.x; task < n_tasks; task += S1_BLOCK) {
-        const int ch = ch_lo + task / Q.g1;
-        const int g1 = task - (ch - ch_lo) * Q.g1;
+    for (int task = tid; task < n_tasks; task += NT) {
+        const int ch = task / Q.g1;
+        const int g1 = task - ch * Q.g1;
         const int i1 = __ldg(Q.i0_1 + g1);
         T w1[W];
 #pragma unroll
@@ -321,7 +331,7 @@ __device__ __forceinline__ void slice_body(const SliceParams<T>& Q, int64_t sl, 
 #pragma unroll
             for (int a = 0; a < W; ++a) win[k][a] = T(0);
         int cur = -(1 << 30);
-        const int g_lo = ch * S1_CHUNK, g_hi = min(Q.g2, g_lo + S1_CHUNK);
+        const int g_lo = g2_lo + ch * sub, g_hi = min(g2_hi, g_lo + sub);
         T* o0 = Q.t0 + sl * out_slice + g1;
         T* o1 = NARR == 2 ? Q.t1 + sl * out_slice + g1 : nullptr;
         // axis-2 table entry of the NEXT output is requested one step ahead: read where it is used, the
@@ -345,7 +355,7 @@ __device__ __forceinline__ void slice_body(const SliceParams<T>& Q, int64_t sl, 
             if (i2 != cur) {
                 const int shift = (i2 > cur && i2 - cur < W) ? i2 - cur : W;
                 for (int s = 0; s < shift; ++s) {
-                    const T* row = S + i1 + Q.n1 * (i2 + (W - shift) + s);
+                    const T* row = S + i1 + Q.n1 * (i2 + (W - shift) + s - r_lo);
 #pragma unroll
                     for (int k = 0; k < NARR; ++k) {
 #pragma unroll
@@ -372,36 +382,42 @@ __device__ __forceinline__ void slice_body(const SliceParams<T>& Q, int64_t sl, 
 template <typename T, int W, int NARR>
 __global__ void __launch_bounds__(S1_BLOCK) grid_slice_kernel(const __grid_constant__ SliceParams<T> Q) {
     extern __shared__ __align__(16) unsigned char s1_smem[];
-    slice_body<T, W, NARR>(Q, blockIdx.x, 0, (Q.g2 + S1_CHUNK - 1) / S1_CHUNK, reinterpret_cast<T*>(s1_smem));
+    slice_body<T, W, NARR, S1_BLOCK>(Q, blockIdx.x, 0, Q.g2, S1_CHUNK, 0, Q.n2, reinterpret_cast<T*>(s1_smem), threadIdx.x);
 }
 
-// ---- both stages in ONE persistent launch -----------------------------------------------------------------
+// ---- both stages in ONE persistent launch (opt-in: DIND_PERSIST=1) -------------------------------------------
 // Run as two kernels, T (config 4: 2 x 537 MB) is written to HBM by stage 1 and read back by stage 2: 2.1 GB of the
 // 4.7 GB the evaluation moves, for 2.4 GB algorithmic.  Alternating the two kernels over L2-sized tiles lost to the
-// per-launch ramp-up and tail.  Here one grid of resident CTAs drains two ordered task queues:
-//   stage-2 tasks (B-tile h, chunk c of the last axis, block bx) — the product;
+// per-launch ramp-up and tail.  Here one grid of resident CTAs drains two ordered task queues,
+// warp by warp:
+//   stage-2 items (B-tile h, chunk c of the last axis, 64 batch columns x 2 rows of g_3) — the product;
 //   stage-1 tasks (B-tile h, slice (i_3, i_4)), in plane order i_4 — the supply.
-// A CTA takes the next stage-2 task, looks up the planes i_4 its chunk needs and, while one of them is incomplete,
-// executes stage-1 tasks itself (demand-driven: the supply runs just ahead of the consumers); once the stage-1 queue
-// is empty it waits.  Every incomplete plane it may wait for was claimed earlier by a CTA that is running, and
-// stage-1 tasks never wait, so there is no deadlock for any t_eval order.  With the stage-2 chunk a few outputs long
-// and B cut into tiles, the live part of T is a handful of planes (tens of MB) that stay in the 126 MB L2 between
-// the store of stage 1 and the loads of stage 2.
-// MEASURED (B200, config 4, 128^4 outputs): 1.64 ms with 8-output chunks and two B-tiles, 1.38 ms with 16, 1.25 ms
-// with 32, 1.17 ms with 32 and no B-tiling — against 1.01 ms for the two separate launches.  Short chunks pay the
-// window start-up of the axis-4 walk (6 planes contracted for 8 outputs instead of 4) and per-task scheduling; long
-// chunks leave more of T live than L2 holds.  The two-launch path therefore stays the default and this kernel is
-// opt-in (DIND_PERSIST=1, parity-tested); making it win needs stage-1 tasks that stage only the rows of u a thin
-// B-tile touches, so that the walk can stay long while the live part of T stays small.
-// Completion is published per (tile, plane) with a device-scope
-// counter (store T; __syncthreads; __threadfence + atomicAdd by one thread) and consumed by a volatile load +
-// __threadfence + __syncthreads; T is then read with ordinary (coherent) loads.
+// A warp takes the next stage-2 item, looks up the planes i_4 its chunk needs and, while one of them is incomplete,
+// executes stage-1 tasks itself in its private slab of shared memory (demand-driven: the supply runs just ahead of
+// the consumers); once the stage-1 queue is empty it waits.  Every incomplete plane it may wait for was claimed
+// earlier by a warp that is running, and stage-1 tasks never wait, so there is no deadlock for any t_eval order.
+// B-tiles are THIN (a few rows of g_2, only the rows of u they touch are staged) and the chunk LONG (32 outputs), so
+// that the planes of T in use (~40 MB) stay in the 126 MB L2 between the stores of stage 1 and the loads of stage 2
+// while the axis-4 walk keeps its length.  Completion is published per (tile, plane) with a device-scope counter
+// (store T; __syncwarp; __threadfence + atomicAdd by one lane) and consumed by volatile loads + __threadfence; T is
+// then read with ordinary (coherent) loads.
+// MEASURED (B200, config 4, 128^4 outputs; two launches: 1.00 ms):
+//   per-CTA scheduling, 8-output chunks, 2 fat B-tiles 1.64 ms; 32-output chunks, no tiling 1.17 ms;
+//   per-CTA scheduling, thin B-tiles, 32-output chunks 1.51 ms (ncu profiles/r2_c4_fused.md: the T READ is gone from
+//     DRAM — 0.87 GB read instead of 1.55 — but DRAM is 33 % busy and as many warps wait at __syncthreads as on memory);
+//   per-warp scheduling (this version)             1.33 ms, the same for 20 ... 200 MB of live T.
+// The saved traffic buys nothing because neither stage is DRAM-bound on its own (stage 2: issue 59 %, FP64 37 %,
+// DRAM 55 %): the evaluation is bound by instruction issue and FP64 dependency latency at 16 warps/SM, and the
+// persistent form adds queue / flag traffic and runs stage 1 at a worse shape.  The two-launch path stays the default.
 template <typename T>
 struct FusedParams {
     SliceParams<T> S;
     BatchParams<T> Q;        // Q.chunk / Q.n_bseg / Q.n_items are per B-tile
     int n_slices, n3;        // slices per tile, slices per plane
-    int n_bt, ch_per_tile;   // B-tiles (ranges of g_2) and stage-1 chunks of g_2 per tile
+    int n_bt, rows_per_tile; // B-tiles = ranges of rows_per_tile outputs along g_2
+    int s1_sub;              // g_2 outputs per lane and step of a stage-1 task
+    int s1_piece;            // g_2 outputs of a tile staged together (their rows of u fit the warp's shared-memory slab)
+    size_t warp_smem_elems;  // elements of T per warp in dynamic shared memory
     int n_chunks4, bx_per;   // stage-2 tasks = n_bt x n_chunks4 x bx_per
     int* ctrl;               // [0] stage-1 queue head, [1] stage-2 queue head, [2 + h * n4 + i_4] finished slices of (tile, plane)
 };
@@ -412,56 +428,79 @@ constexpr int FU_MAXCHUNK = 32;
 
 template <typename T, int W, bool NURBS>
 __global__ void __launch_bounds__(FU_BLOCK, 2) grid_split_fused_kernel(const __grid_constant__ FusedParams<T> F) {
+    // Everything is WARP-granular: a warp claims a stage-2 item (64 batch columns x 2 rows of g_3 x one chunk of the
+    // last axis), supplies missing planes by executing stage-1 tasks on its own (its private slab of shared memory),
+    // and never meets a CTA barrier — the first version scheduled per CTA and ncu showed as many warps waiting at
+    // __syncthreads (1.9 per issue cycle) as on memory.
     extern __shared__ __align__(16) unsigned char s1_smem[];
-    T* S = reinterpret_cast<T*>(s1_smem);
-    __shared__ int s_i0[FU_MAXCHUNK];
-    __shared__ T s_w[FU_MAXCHUNK * W];
-    __shared__ int s_task, s_s1, s_ready;
+    __shared__ int s_i0[FU_BLOCK / 32][FU_MAXCHUNK];
+    __shared__ T s_w[FU_BLOCK / 32][FU_MAXCHUNK * W];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T* S = reinterpret_cast<T*>(s1_smem) + (size_t)warp * F.warp_smem_elems;
+    constexpr int NARR = NURBS ? 2 : 1;
     const int n4 = F.Q.n4;
-    const int n_tasks2 = F.n_bt * F.n_chunks4 * F.bx_per, n_tasks1 = F.n_bt * F.n_slices;
+    const int per_tc = F.Q.n_items;                                   // stage-2 items per (tile, chunk)
+    const int n_tasks2 = F.n_bt * F.n_chunks4 * per_tc, n_tasks1 = F.n_bt * F.n_slices;
     volatile int* done = F.ctrl + 2;
     for (;;) {
-        if (threadIdx.x == 0) s_task = atomicAdd(F.ctrl + 1, 1);
-        __syncthreads();
-        const int t2 = s_task;
+        int t2 = 0;
+        if (lane == 0) t2 = atomicAdd(F.ctrl + 1, 1);
+        t2 = __shfl_sync(0xffffffffu, t2, 0);
         if (t2 >= n_tasks2) break;
-        const int h = t2 / (F.n_chunks4 * F.bx_per);
-        const int r = t2 - h * (F.n_chunks4 * F.bx_per);
-        const int c = r / F.bx_per, bx = r - c * F.bx_per;
+        const int h = t2 / (F.n_chunks4 * per_tc);
+        const int r = t2 - h * (F.n_chunks4 * per_tc);
+        const int c = r / per_tc, item = r - c * per_tc;
         for (;;) {
-            if (threadIdx.x < 32) {
-                // planes the chunk needs: [min, max + W) of its first nodes; lane l looks at output l and at plane l
-                const int g_lo = c * F.Q.chunk, g_hi = min(F.Q.g4, g_lo + F.Q.chunk);
-                const int lane = threadIdx.x;
-                const int p0 = __ldg(F.Q.i0_4 + min(g_lo + lane, g_hi - 1));
-                const int p_lo = __reduce_min_sync(0xffffffffu, p0), p_hi = __reduce_max_sync(0xffffffffu, p0) + W;
-                int ready = 1;
-                for (int p = p_lo + lane; p < p_hi; p += 32) ready = ready && done[h * n4 + p] >= F.n3;
-                ready = __all_sync(0xffffffffu, ready);
-                if (lane == 0) {
-                    s_ready = ready;
-                    s_s1 = ready ? -1 : atomicAdd(F.ctrl, 1);
-                    if (ready) __threadfence();
+            // planes the chunk needs: [min, max + W) of its first nodes; lane l looks at output l and at plane l
+            const int g_lo = c * F.Q.chunk, g_hi = min(F.Q.g4, g_lo + F.Q.chunk);
+            const int p0 = __ldg(F.Q.i0_4 + min(g_lo + lane, g_hi - 1));
+            const int p_lo = __reduce_min_sync(0xffffffffu, p0), p_hi = __reduce_max_sync(0xffffffffu, p0) + W;
+            int ready = 1;
+            for (int p = p_lo + lane; p < p_hi; p += 32) ready = ready && done[h * n4 + p] >= F.n3;
+            ready = __all_sync(0xffffffffu, ready);
+            if (ready) {
+                __threadfence();
+                break;
+            }
+            int s1 = 0;
+            if (lane == 0) s1 = atomicAdd(F.ctrl, 1);
+            s1 = __shfl_sync(0xffffffffu, s1, 0);
+            if (s1 >= n_tasks1) {      // nothing left to supply: the missing planes are being written by other warps
+                __nanosleep(200);
+                continue;
+            }
+            const int h1 = s1 / F.n_slices, sl = s1 - h1 * F.n_slices;
+            const int t_lo = h1 * F.rows_per_tile, t_hi = min(F.S.g2, t_lo + F.rows_per_tile);
+            // the tile's outputs in pieces whose rows of u fit the warp's shared-memory slab
+            for (int g2_lo = t_lo; g2_lo < t_hi; g2_lo += F.s1_piece) {
+                const int g2_hi = min(t_hi, g2_lo + F.s1_piece);
+                int lo = 1 << 30, hi = -1;
+                for (int g = g2_lo + lane; g < g2_hi; g += 32) {
+                    const int rr = __ldg(F.S.i0_2 + g);
+                    lo = min(lo, rr);
+                    hi = max(hi, rr);
+                }
+                lo = __reduce_min_sync(0xffffffffu, lo);
+                hi = __reduce_max_sync(0xffffffffu, hi);
+                int r_n = hi + W - lo;
+                if ((size_t)r_n * F.S.n1 * NARR > F.warp_smem_elems) {   // rows too far apart (unsorted t_eval): one output at a time
+                    for (int g = g2_lo; g < g2_hi; ++g) {
+                        const int rr = __ldg(F.S.i0_2 + g);
+                        slice_body<T, W, NARR, 32>(F.S, sl, g, g + 1, 1, rr, W, S, lane);
+                        __syncwarp();
+                    }
+                } else {
+                    slice_body<T, W, NARR, 32>(F.S, sl, g2_lo, g2_hi, F.s1_sub, lo, r_n, S, lane);
+                    __syncwarp();
                 }
             }
-            __syncthreads();
-            if (s_ready) break;
-            const int s1 = s_s1;
-            if (s1 < n_tasks1) {
-                const int h1 = s1 / F.n_slices, sl = s1 - h1 * F.n_slices;
-                slice_body<T, W, NURBS ? 2 : 1>(F.S, sl, h1 * F.ch_per_tile, (h1 + 1) * F.ch_per_tile, S);
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    __threadfence();
-                    atomicAdd(F.ctrl + 2 + h1 * n4 + sl / F.n3, 1);
-                }
-            } else {
-                __nanosleep(256);
+            if (lane == 0) {
+                __threadfence();
+                atomicAdd(F.ctrl + 2 + h1 * n4 + sl / F.n3, 1);
             }
-            __syncthreads();
         }
-        batch_body<T, W, W, NURBS, FU_BLOCK, true>(F.Q, bx, c, h * F.Q.n_bseg, s_i0, s_w);
-        __syncthreads();
+        batch_body<T, W, W, NURBS, 32, true>(F.Q, item, c, h * F.Q.n_bseg, s_i0[warp], s_w[warp], lane);
+        __syncwarp();
     }
 }
 
@@ -505,29 +544,39 @@ bool fused_plan(const EvalParams<T>& P, FusedParams<T>& F, size_t ctrl_ints_cap)
     const int64_t g1 = P.dim[0].n_eval, g2 = P.dim[1].n_eval;
     const int n3 = P.dim[2].n_u, n4 = P.dim[3].n_u;
     const int narr = P.wts ? 2 : 1;
-    // B-tiles: ranges of g_2 (whole stage-1 chunks) so that a plane of T of one tile is at most ~10 MB
-    const int n_ch2 = (int)((g2 + S1_CHUNK - 1) / S1_CHUNK);
-    if (g2 % S1_CHUNK != 0) return false;
-    int n_bt = 1;
-    while (n_bt < n_ch2 && n_ch2 % (n_bt * 2) == 0 &&
-           (double)g1 * (g2 / n_bt) * n3 * sizeof(T) * narr > ((P.knobs && P.knobs->pf1 > 0) ? P.knobs->pf1 * 1.0e6 : 10.0e6)) n_bt *= 2;
-    const int64_t b_tile = g1 * (g2 / n_bt);
+    // stage-2 chunk along the last axis: long (32 outputs), so that the window start-up of the walk is amortised;
+    // B-tiles THIN (a few rows of g_2), so that the planes of T a chunk needs — about chunk * n4 / g4 + W of them —
+    // stay within ~40 MB of L2 for the whole tile (experiment knobs: DIND_CHUNK, DIND_PF1 = MB)
+    int chunk = (P.knobs && P.knobs->chunk > 0) ? P.knobs->chunk : 32;
+    chunk = std::max(1, std::min(chunk, FU_MAXCHUNK));
+    const double planes = (double)chunk * n4 / (double)P.dim[3].n_eval + W;
+    const double budget = ((P.knobs && P.knobs->pf1 > 0) ? P.knobs->pf1 : 40) * 1.0e6;
+    int rows = (int)g2;
+    while (rows > 1 && ((double)g1 * rows * n3 * planes * sizeof(T) * narr > budget || g2 % rows != 0)) --rows;
+    const int n_bt = (int)(g2 / rows);
+    const int64_t b_tile = g1 * rows;
     if (b_tile % (32 * SB_VB) != 0) return false;
     if ((size_t)(2 + n_bt * n4) > ctrl_ints_cap) return false;
     F.n_slices = n3 * n4;
     F.n3 = n3;
     F.n_bt = n_bt;
-    F.ch_per_tile = n_ch2 / n_bt;
-    // stage-2 chunk along the last axis: short, so that few planes of T are live (experiment knob DIND_CHUNK)
-    int chunk = (P.knobs && P.knobs->chunk > 0) ? P.knobs->chunk : 8;
-    chunk = std::max(1, std::min(chunk, FU_MAXCHUNK));
+    F.rows_per_tile = rows;
+    // stage 1 runs per warp: its slab of shared memory (2 CTAs/SM x 8 warps share ~200 KB) holds the rows of u that a
+    // piece of the tile's g_2 outputs touches — about piece * n2 / g2 + W rows of n1 elements (x2 for NURBS)
+    const int n1 = P.dim[0].n_u, n2 = P.dim[1].n_u;
+    F.warp_smem_elems = (size_t)(100 * 1024 / (FU_BLOCK / 32)) / sizeof(T);
+    if ((size_t)W * n1 * narr > F.warp_smem_elems) return false;
+    int piece = rows;
+    while (piece > 1 && ((double)piece * n2 / (double)g2 + W + 1) * n1 * narr > (double)F.warp_smem_elems) piece = (piece + 1) / 2;
+    F.s1_piece = piece;
+    F.s1_sub = std::min(piece, 8);
     F.Q.chunk = chunk;
     F.n_chunks4 = (int)((P.dim[3].n_eval + chunk - 1) / chunk);
     F.Q.n_bseg = (int)(b_tile / (32 * SB_VB));
     const int64_t items = (int64_t)F.Q.n_bseg * ((P.dim[2].n_eval + 1) / 2);
     F.Q.n_items = (int)items;
-    F.bx_per = (int)((items + FU_BLOCK / 32 - 1) / (FU_BLOCK / 32));
-    return (int64_t)n_bt * F.n_chunks4 * F.bx_per < (1LL << 30);
+    F.bx_per = (int)items;   // stage-2 tasks are single items (one warp each)
+    return (int64_t)n_bt * F.n_chunks4 * items < (1LL << 30);
 }
 
 }  // namespace
@@ -632,12 +681,11 @@ cudaError_t launch_grid_split(const EvalParams<T>& P, void* scratch, cudaStream_
         if (fused_plan<T>(P, F, FUSED_CTRL_BYTES / sizeof(int))) {
             const size_t ctrl_bytes = (size_t)(2 + F.n_bt * n4) * sizeof(int);
             if ((e = cudaMemsetAsync(F.ctrl, 0, ctrl_bytes, s)) != cudaSuccess) return e;
-            const size_t smem = (size_t)(td ? 2 : 1) * n1 * n2 * sizeof(T);
+            const size_t smem = F.warp_smem_elems * sizeof(T) * (FU_BLOCK / 32);
             int dev = 0, n_sm = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            const int n_tasks2 = F.n_bt * F.n_chunks4 * F.bx_per;
-            const int grid = std::min(n_tasks2, 2 * n_sm);
+            const int grid = 2 * n_sm;
 #define DIND_FUSED(WW, NU)                                                                                                  \
     {                                                                                                                      \
         if ((e = cudaFuncSetAttribute(grid_split_fused_kernel<T, WW, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
