@@ -144,7 +144,7 @@ struct Knobs {
     int pf = 1;          // DIND_PF: one-run-ahead register prefetch of the pencil kernel
     int pf1 = -1;        // DIND_PF1: L1 prefetch distance (-1 = default of the instantiation)
     int l2_warm = -1;    // DIND_L2_WARM: bulk L2 warm-up of u (-1 = default)
-    int c3_tile = -1;    // DIND_C3_TILE: points per thread of the cell-sorted cubic kernel (-1 = default)
+    int c3_tile = -1;    // DIND_C3_TILE: points per work item of the tile kernels (0 = one-point kernels, -1 = default)
     bool no_lut = false, no_split = false, no_cells = false, no_aos = false, no_small = false, no_slice = false;
     bool persist = false;      // DIND_PERSIST=1: the persistent two-stage 4-D grid kernel instead of two launches
 };

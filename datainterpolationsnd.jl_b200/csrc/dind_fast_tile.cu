@@ -437,7 +437,7 @@ cudaError_t launch_linear_tile(const EvalParams<float>& P, cudaStream_t s) {
 // item-major copies of the plan's inputs (see unstructured_tile_kernel)
 template <typename T, int N>
 __global__ void __launch_bounds__(256) plan_item_layout_kernel(const __grid_constant__ EvalParams<T> P, int pts, uint32_t* __restrict__ item_cells,
-                                                               T* const* __restrict__ item_t_unused, T* t0, T* t1, T* t2, T* t3, T* t4, T* t5) {
+                                                               T* t0, T* t1, T* t2, T* t3, T* t4, T* t5) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= P.n_items) return;
     const uint32_t s0 = P.items[i], s1 = P.items[i + 1];
@@ -482,7 +482,9 @@ int tile_points_per_item(const EvalParams<T>& P, bool gradient) {
     const int forced = P.knobs ? P.knobs->c3_tile : -1;
     if (forced == 0) return 0;
     if (gradient) return (sizeof(T) == 8 && N == 3 && W == 4 && C == 3) ? 2 : 0;   // 12 accumulators per point: two points per item
-    if (sizeof(T) == 8 && N == 3 && W == 4 && C == 3) return (forced == 2 || forced == 3 || forced == 4) ? forced : (forced == 32 ? 3 : (forced == 22 ? 2 : 3));
+    // 3 points per item (168 registers, 3 CTAs/SM): 29.4 Gpoints/s on config 3; 2 per item 28.6, 4 per item (254
+    // registers) 16.3 — DESIGN.md §4.  DIND_C3_TILE=2 keeps the 2-point variant reachable for experiments.
+    if (sizeof(T) == 8 && N == 3 && W == 4 && C == 3) return forced == 2 ? 2 : 3;
     if (sizeof(T) == 4 && N == 5 && W == 2 && C == 4) {
         bool linear = true;
         double cells_total = 1.0;
@@ -491,7 +493,7 @@ int tile_points_per_item(const EvalParams<T>& P, bool gradient) {
             cells_total *= (double)(P.dim[d].n_u - 1);
         }
         if (!linear) return 0;
-        if (forced == 2 || forced == 4) return forced;
+        if (forced == 4) return 4;   // experiment knob DIND_C3_TILE=4
         // expected points per cell for points spread over the table: hardly any -> no items (one point per thread).
         // 2 points per item at 8 CTAs/SM beats 4 per item (166 registers, 3 CTAs/SM) at every density measured:
         // 1e8 points (3.5 per cell) 57.0 vs 43.9 Gpoints/s, 5e8 points (17 per cell) 66.6 vs 54.0 (63.6 at 4 CTAs/SM)
@@ -518,26 +520,16 @@ bool try_eval_fast_tile(const EvalParams<T>& P, bool gradient, cudaStream_t s, c
     }
     if constexpr (sizeof(T) == 4) {
         if (N == 5 && W == 2 && C == 4) {
-            const int forced = P.knobs ? P.knobs->chunk : 0;   // experiment: DIND_CHUNK=6|8 -> CTAs per SM
-            if (PT == 2 && forced == 6) { *err = launch_linear_tile<5, 2, 6>(P, s); *name = "linear_tile<N=5,C=4,PT=2,ffma2,6cta>"; return true; }
-            if (PT == 2 && forced == 8) { *err = launch_linear_tile<5, 2, 8>(P, s); *name = "linear_tile<N=5,C=4,PT=2,ffma2,8cta>"; return true; }
-            if (PT == 2 && forced == 5) { *err = launch_linear_tile<5, 2, 5>(P, s); *name = "linear_tile<N=5,C=4,PT=2,ffma2,5cta>"; return true; }
             // 8 CTAs/SM (64 registers, no spills): the kernel waits on gathers, resident warps are what hides them
             // (plan order, 1e8 points: 5 CTAs 52.4, 6 CTAs 53.6, 8 CTAs 57.0 Gpoints/s)
             if (PT == 2) { *err = launch_linear_tile<5, 2, 8>(P, s); *name = "linear_tile<N=5,C=4,PT=2,ffma2>"; return true; }
-            if (PT == 4 && forced == 4) { *err = launch_linear_tile<5, 4, 4>(P, s); *name = "linear_tile<N=5,C=4,PT=4,ffma2,4cta>"; return true; }
-            if (PT == 4 && forced == 5) { *err = launch_linear_tile<5, 4, 5>(P, s); *name = "linear_tile<N=5,C=4,PT=4,ffma2,5cta>"; return true; }
-            if (PT == 4) { *err = launch_linear_tile<5, 4, 3>(P, s); *name = "linear_tile<N=5,C=4,PT=4,ffma2>"; return true; }
+            if (PT == 4) { *err = launch_linear_tile<5, 4, 4>(P, s); *name = "linear_tile<N=5,C=4,PT=4,ffma2>"; return true; }
         }
     }
     if constexpr (sizeof(T) == 8) {
         if (N == 3 && W == 4 && C == 3) {
-            const int forced = P.knobs ? P.knobs->c3_tile : -1;
-            if (forced == 32) { *err = launch_tile<T, 3, 4, 3, 3, 4>(P, s); *name = "unstructured_tile<N=3,W=4,C=3,PT=3,4cta>"; return true; }
-            if (forced == 22) { *err = launch_tile<T, 3, 4, 3, 2, 5>(P, s); *name = "unstructured_tile<N=3,W=4,C=3,PT=2,5cta>"; return true; }
             if (PT == 2) { *err = launch_tile<T, 3, 4, 3, 2, 4>(P, s); *name = "unstructured_tile<N=3,W=4,C=3,PT=2>"; return true; }
             if (PT == 3) { *err = launch_tile<T, 3, 4, 3, 3, 3>(P, s); *name = "unstructured_tile<N=3,W=4,C=3,PT=3>"; return true; }
-            if (PT == 4) { *err = launch_tile<T, 3, 4, 3, 4, 2>(P, s); *name = "unstructured_tile<N=3,W=4,C=3,PT=4>"; return true; }
         }
     }
     return false;
@@ -550,12 +542,12 @@ cudaError_t plan_item_layout(const EvalParams<T>& P, int pts, uint32_t* item_cel
     T* t[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     for (int d = 0; d < P.n_in && d < 6; ++d) t[d] = item_t[d];
     switch (P.n_in) {
-        case 1: plan_item_layout_kernel<T, 1><<<nb, 256, 0, s>>>(P, pts, item_cells, nullptr, t[0], t[1], t[2], t[3], t[4], t[5]); break;
-        case 2: plan_item_layout_kernel<T, 2><<<nb, 256, 0, s>>>(P, pts, item_cells, nullptr, t[0], t[1], t[2], t[3], t[4], t[5]); break;
-        case 3: plan_item_layout_kernel<T, 3><<<nb, 256, 0, s>>>(P, pts, item_cells, nullptr, t[0], t[1], t[2], t[3], t[4], t[5]); break;
-        case 4: plan_item_layout_kernel<T, 4><<<nb, 256, 0, s>>>(P, pts, item_cells, nullptr, t[0], t[1], t[2], t[3], t[4], t[5]); break;
-        case 5: plan_item_layout_kernel<T, 5><<<nb, 256, 0, s>>>(P, pts, item_cells, nullptr, t[0], t[1], t[2], t[3], t[4], t[5]); break;
-        case 6: plan_item_layout_kernel<T, 6><<<nb, 256, 0, s>>>(P, pts, item_cells, nullptr, t[0], t[1], t[2], t[3], t[4], t[5]); break;
+        case 1: plan_item_layout_kernel<T, 1><<<nb, 256, 0, s>>>(P, pts, item_cells, t[0], t[1], t[2], t[3], t[4], t[5]); break;
+        case 2: plan_item_layout_kernel<T, 2><<<nb, 256, 0, s>>>(P, pts, item_cells, t[0], t[1], t[2], t[3], t[4], t[5]); break;
+        case 3: plan_item_layout_kernel<T, 3><<<nb, 256, 0, s>>>(P, pts, item_cells, t[0], t[1], t[2], t[3], t[4], t[5]); break;
+        case 4: plan_item_layout_kernel<T, 4><<<nb, 256, 0, s>>>(P, pts, item_cells, t[0], t[1], t[2], t[3], t[4], t[5]); break;
+        case 5: plan_item_layout_kernel<T, 5><<<nb, 256, 0, s>>>(P, pts, item_cells, t[0], t[1], t[2], t[3], t[4], t[5]); break;
+        case 6: plan_item_layout_kernel<T, 6><<<nb, 256, 0, s>>>(P, pts, item_cells, t[0], t[1], t[2], t[3], t[4], t[5]); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -651,6 +651,39 @@ def test_cell_sorted_plan_packed_cells_and_search_agree(D, dtype, case, monkeypa
         i.close()
 
 
+@pytest.mark.parametrize("tile", ["0", "2", "4"])
+@pytest.mark.parametrize("shape", ["cubic3d", "linear5d"])
+def test_tile_kernel_variants_are_bit_identical(D, tile, shape, monkeypatch):
+    """DIND_C3_TILE selects the points per work item of the plan's tile kernels (0: one point per thread; 2 / 3 for
+    the cubic kernel; 2 / 4 for the packed-FMA linear kernel).  Every variant must give the unsorted evaluation's bits,
+    in original and in plan order, for values and a first derivative, and the fused gradient likewise."""
+    rng = np.random.default_rng(1234)
+    if shape == "cubic3d":
+        kinds, degrees, n_knots, out_dims, dtype = ("bspline",) * 3, (3, 3, 3), (7, 6, 8), (3,), np.float64
+    else:
+        kinds, degrees, n_knots, out_dims, dtype = ("linear",) * 5, (0,) * 5, (4, 5, 4, 3, 5), (4,), np.float32
+    ts, u, _ = _case(rng, kinds, degrees, n_knots, out_dims, dtype)
+    xs = H.zipped_queries(rng, ts, 40000, dtype)      # ~100 points per cell: items of every length
+    n = len(kinds)
+    mk = lambda: D.NDInterpolation(u, H.make_dims(D, kinds, ts, xs, degrees, None, max_deriv=[1] * n))
+    ref_itp = mk()
+    monkeypatch.setenv("DIND_C3_TILE", tile)
+    itp = mk()                                        # the knob is read once, in dind_create
+    monkeypatch.delenv("DIND_C3_TILE")
+    orders = (0,) * (n - 1) + (1,)
+    for o in (None, orders):
+        ref = D.eval_unstructured(ref_itp, derivative_orders=o)
+        got = D.eval_unstructured(itp, derivative_orders=o, flags=CELL_SORTED)
+        assert np.array_equal(ref, got), (o, itp.last_kernel)
+        po = D.eval_unstructured(itp, derivative_orders=o, flags=CELL_SORTED | 32)
+        assert np.array_equal(ref[itp.plan_permutation()], po), (o, itp.last_kernel)
+        expect = ("unstructured_aos" if tile == "0" else ("unstructured_tile" if shape == "cubic3d" else "linear_tile"))
+        assert itp.last_kernel.startswith(expect), itp.last_kernel
+    assert np.array_equal(D.eval_unstructured_gradient(ref_itp), D.eval_unstructured_gradient(itp, flags=CELL_SORTED))
+    itp.close()
+    ref_itp.close()
+
+
 def test_nurbs_weights_with_constant_axis(D):
     """BASELINE config 4 names NURBS weights with mixed Constant(left=true)/BSpline dimensions: no
     reference semantics — defined as the tensor product of the per-dimension stencils
