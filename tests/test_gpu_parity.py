@@ -664,6 +664,8 @@ def test_tile_kernel_variants_are_bit_identical(D, tile, shape, monkeypatch):
         kinds, degrees, n_knots, out_dims, dtype = ("linear",) * 5, (0,) * 5, (4, 5, 4, 3, 5), (4,), np.float32
     ts, u, _ = _case(rng, kinds, degrees, n_knots, out_dims, dtype)
     xs = H.zipped_queries(rng, ts, 40000, dtype)      # ~100 points per cell: items of every length
+    special = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, np.finfo(dtype).max], dtype=dtype)
+    xs = [np.concatenate([x, np.roll(special, d)]).astype(dtype) for d, x in enumerate(xs)]   # non-finite coordinates too
     n = len(kinds)
     mk = lambda: D.NDInterpolation(u, H.make_dims(D, kinds, ts, xs, degrees, None, max_deriv=[1] * n))
     ref_itp = mk()
@@ -674,12 +676,14 @@ def test_tile_kernel_variants_are_bit_identical(D, tile, shape, monkeypatch):
     for o in (None, orders):
         ref = D.eval_unstructured(ref_itp, derivative_orders=o)
         got = D.eval_unstructured(itp, derivative_orders=o, flags=CELL_SORTED)
-        assert np.array_equal(ref, got), (o, itp.last_kernel)
+        assert np.array_equal(ref, got, equal_nan=True), (o, itp.last_kernel)
         po = D.eval_unstructured(itp, derivative_orders=o, flags=CELL_SORTED | 32)
-        assert np.array_equal(ref[itp.plan_permutation()], po), (o, itp.last_kernel)
+        assert np.array_equal(ref[itp.plan_permutation()], po, equal_nan=True), (o, itp.last_kernel)
         expect = ("unstructured_aos" if tile == "0" else ("unstructured_tile" if shape == "cubic3d" else "linear_tile"))
         assert itp.last_kernel.startswith(expect), itp.last_kernel
-    assert np.array_equal(D.eval_unstructured_gradient(ref_itp), D.eval_unstructured_gradient(itp, flags=CELL_SORTED))
+    assert np.array_equal(D.eval_unstructured_gradient(ref_itp), D.eval_unstructured_gradient(itp, flags=CELL_SORTED), equal_nan=True)
+    # and against the oracle (values), NaN pattern included
+    H.assert_close(D.eval_unstructured(itp, flags=CELL_SORTED), H.oracle_eval(kinds, ts, u, xs, degrees=degrees), dtype)
     itp.close()
     ref_itp.close()
 
