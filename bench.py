@@ -510,6 +510,7 @@ def run_gpu(args, wl, rank, world, local_rank):
 # ---- the other BASELINE configs at their named sizes, in the same JSON line ---------------------------------------
 FMA_PEAK_TFMA = {"f64": 17.6, "f32": 32.3}   # register-resident FMA microbenchmark on B200 (scripts/microbench_fma.cu; profiles/r2_microbench.txt)
 C3_FP64_OPS_PER_POINT = 378                  # 285 DFMA + 51 DADD + 42 DMUL per point and evaluation (ncu instruction mix)
+C3_GRADIENT_FP64_OPS_PER_POINT = 756         # fused value + 3 partials: contraction 384 + 144 + 48 FMA, order-0 and order-1 basis ~180
 
 
 def _time_steps(torch, dist, stream, world, fn, steps, warmup):
@@ -605,11 +606,11 @@ def bench_unstructured_family(D, torch, dist, wl, rank, world, local_rank, steps
         kernel = itp.last_kernel
         (ms,) = _max_over_ranks(torch, dist, world, dev, [ms])
         if wl.key == "c3":
-            evals = (n_in + 1) if mode.startswith("gradient") else 1
-            fma_bound = FMA_PEAK_TFMA["f64"] * 1e12 / (C3_FP64_OPS_PER_POINT * evals) / 1e9   # Gpoints/s per GPU
+            ops = C3_GRADIENT_FP64_OPS_PER_POINT if mode.startswith("gradient") else C3_FP64_OPS_PER_POINT
+            fma_bound = FMA_PEAK_TFMA["f64"] * 1e12 / ops / 1e9   # Gpoints/s per GPU
             extra["roofline_fma"] = {"bound": "fp64 pipe", "peak_Gpoints_per_s_per_gpu": round(fma_bound, 1),
                                      "frac": round(n / (ms * 1e-3) / 1e9 / fma_bound, 4),
-                                     "note": "378 FP64 operations per point and evaluation at the measured 17.6 T/s (DESIGN.md §6)"}
+                                     "note": f"{ops} FP64 operations per point at the measured 17.6 T/s (DESIGN.md §6)"}
         res[mode] = _entry(wl, ms, n_total, alg, per_step, kernel, extra)
         if mode.startswith("gradient"):
             del gout

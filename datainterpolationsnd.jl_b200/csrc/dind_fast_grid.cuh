@@ -474,7 +474,10 @@ cudaError_t launch_pencil_cfg(const EvalParams<T>& P, cudaStream_t s) {
     dim3 grid((unsigned)bx, (unsigned)((n_last + chunk - 1) / chunk));
     // L1 prefetch distance, measured: config 2 0 -> 0.133 ms, 1..3 -> 0.122 ms, 6 -> 0.128 ms; every W = 2 / 3 case
     // of scripts/sanity_perf.py gains 2-16 %, the W = 4 cases (long runs, 3-4x upsampling) lose 3-6 %
-    constexpr int pf1_default = W <= 3 ? 4 : 0;   // 4 CTAs/SM: distance 4..8 beats 2 by 2 % on config 2 (L1 has the room)
+    // W = 4: the L1 prefetch pays when the walk changes node often (<= ~2.5 outputs per node of the last axis:
+    // tricubic F32 256^3 -> 512^3 520 -> 588 Gpoints/s) and costs 6-8 % on long runs (128^3 -> 384^3: 810 -> 763)
+    const bool dense_walk = (double)n_last <= 2.5 * (double)P.dim[N - 1].n_u;
+    const int pf1_default = W <= 3 ? 4 : (dense_walk ? 2 : 0);   // 4 CTAs/SM: distance 4..8 beats 2 by 2 % on config 2 (L1 has the room)
     // warm L2 with u when it (plus the NURBS weights) fits comfortably and the pointers allow bulk prefetch; with the
     // L1 prefetch running ahead of the walk the warm-up only competes with it (config 2: 0.116 with, 0.114 ms without)
     const size_t u_bytes = (size_t)P.u_comp_stride * (P.n_comp + (P.wts ? 1 : 0)) * sizeof(T);

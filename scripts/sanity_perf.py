@@ -16,7 +16,12 @@ def knots(rng, n, dtype):
     return np.cumsum(0.5 + rng.random(n)).astype(dtype)
 
 
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""   # substring filter: python scripts/sanity_perf.py "tricubic F32 256"
+
+
 def run(name, kinds, degrees, n_u, n_grid, dtype, nurbs=False, out_dims=()):
+    if ONLY and ONLY not in name:
+        return
     rng = np.random.default_rng(0)
     tdt = torch.float32 if dtype == np.float32 else torch.float64
     ts, dims = [], []
@@ -60,6 +65,9 @@ if __name__ == "__main__":
     run("2-D bicubic F64 1024^2 -> 4096^2", ["bspline"] * 2, [3, 3], (1024, 1024), (4096, 4096), f64)
     run("3-D trilinear F64 256^3 -> 512^3", ["linear"] * 3, [0] * 3, (256,) * 3, (512,) * 3, f64)
     run("3-D tricubic F32 128^3 -> 384^3", ["bspline"] * 3, [3] * 3, (128,) * 3, (384,) * 3, f32)
+    run("3-D tricubic F64 128^3 -> 384^3", ["bspline"] * 3, [3] * 3, (128,) * 3, (384,) * 3, f64)
+    run("3-D tricubic F64 128^3 -> 256^3, 3 comps (config-3 u)", ["bspline"] * 3, [3] * 3, (128,) * 3, (256,) * 3, f64, out_dims=(3,))
+    run("3-D tricubic F32 256^3 -> 512^3", ["bspline"] * 3, [3] * 3, (256,) * 3, (512,) * 3, f32)
     run("3-D triquadratic F64 128^3 -> 256^3, 3 comps", ["bspline"] * 3, [2] * 3, (128,) * 3, (256,) * 3, f64, out_dims=(3,))
     run("3-D trilinear F32 256^3 -> 500x333x250 (odd)", ["linear"] * 3, [0] * 3, (256,) * 3, (500, 333, 250), f32)
     run("4-D linear F32 64^4 -> 128^4", ["linear"] * 4, [0] * 4, (64,) * 4, (128,) * 4, f32)
