@@ -43,6 +43,8 @@ constexpr unsigned FLAG_BUILD_ONLY = 1u << 30;
 constexpr unsigned DIND_FLAG_PUBLIC_MASK = ~(FLAG_OUT_MAPPED | FLAG_BUILD_ONLY);
 constexpr size_t SMALL_BYTES = 64 << 10;    // staging size of the small-batch path
 constexpr int64_t SMALL_POINTS = 2048;
+constexpr size_t REC_MIN_TABLE_BYTES = 96u << 20;   // tables below this stay L2-resident: the plain gather is fine
+constexpr size_t REC_MAX_BYTES = 32ull << 30;       // cap of the cell-record copy of u
 
 Knobs read_knobs() {
     auto geti = [](const char* name, int dflt) {
@@ -62,6 +64,7 @@ Knobs read_knobs() {
     k.no_small = getenv("DIND_NO_SMALL") != nullptr;
     k.no_slice = getenv("DIND_NO_SLICE") != nullptr;
     k.persist = getenv("DIND_PERSIST") != nullptr;
+    k.rec = geti("DIND_REC", -1);
     return k;
 }
 
@@ -453,6 +456,32 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         }
         P.u_aos = (const T*)h->u_aos.p;
     }
+    // multilinear table larger than L2 at iid points: gather from the cell-record copy (one contiguous block per
+    // point instead of 2^(N-1) row segments).  Built when one evaluation already repays the pass that writes it
+    // (the gather saves ~1 KB of DRAM traffic per point), kept until the next dind_set_u.
+    if (use_aos && !gradient && h->knobs.rec != 0 && rec_supported<T>(P)) {
+        if (!h->u_rec_valid && !h->u_rec_declined) {
+            const size_t bytes = rec_table_bytes<T>(P);
+            const size_t aos_bytes = (size_t)h->comp_stride * aos_node_stride((int)h->n_comp) * sizeof(T);
+            const bool want = h->knobs.rec == 1 || (aos_bytes > REC_MIN_TABLE_BYTES && (double)n_points * 1024.0 >= (double)bytes);
+            if (want) {
+                size_t free_b = 0, total_b = 0;
+                CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+                if (bytes <= REC_MAX_BYTES && bytes <= free_b / 2 && h->u_rec.ensure(bytes) == cudaSuccess) {
+                    CUDA_TRY(launch_rec_build<T>(P, (T*)h->u_rec.p, h->stream));
+                    h->launches += 1;
+                    h->u_rec_valid = true;
+                } else {
+                    (void)cudaGetLastError();
+                    h->u_rec_declined = true;
+                }
+            }
+        }
+        if (h->u_rec_valid) {
+            P.u_rec = (const T*)h->u_rec.p;
+            rec_fill_strides<T>(P);
+        }
+    }
     // cell-sorted plan: the work-item schedule of the tile kernels (<= pts consecutive points of one cell per thread)
     dind_interp_s::PlanItems* IT = nullptr;
     if (use_aos && P.cells) {
@@ -527,6 +556,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         for (int d = 0; d < N; ++d) Q.dim[d].t_eval = (const T*)IT->t[d].p;
         handled = try_eval_fast_tile<T>(Q, false, h->stream, &name, &err, &nlaunch);
     }
+    if (use_aos && !handled && P.u_rec) handled = try_eval_fast_unstructured_rec<T>(P, h->stream, &name, &err, &nlaunch);
     if (use_aos && !handled) handled = try_eval_fast_unstructured_aos<T>(P, h->stream, &name, &err, &nlaunch);
     if (split && !handled) {
         err = launch_grid_split<T>(P, h->split_scratch.p, h->stream, &name, &nlaunch);
@@ -691,7 +721,7 @@ int dind_destroy(dind_handle_t h) {
         h->dims[d].release();
         h->pts_stage[d].release();
     }
-    h->u_owned.release(); h->w_owned.release(); h->uw.release(); h->u_aos.release(); h->split_scratch.release(); h->out_stage[0].release(); h->out_stage[1].release();
+    h->u_owned.release(); h->w_owned.release(); h->uw.release(); h->u_aos.release(); h->u_rec.release(); h->split_scratch.release(); h->out_stage[0].release(); h->out_stage[1].release();
     if (h->small_host) cudaFreeHost(h->small_host);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_kernel) cudaEventDestroy(h->ev_kernel);
@@ -859,6 +889,7 @@ int dind_set_u(dind_handle_t h, const void* u, const int64_t* dims, int ndims, u
     h->u_set = true;
     h->uw_valid = false;
     h->u_aos_valid = false;
+    h->u_rec_valid = h->u_rec_declined = false;
     return DIND_OK;
 }
 

@@ -135,6 +135,8 @@ struct DimParams {
     // [cell_shift, cell_shift + popc(cell_mask)) of the point's cell word; cell_add turns it into the reference's
     // 1-based idx (Linear: + 1, BSpline: + degree + 1)
     int32_t cell_shift, cell_mask, cell_add;
+    // cell-record copy of u (EvalParams::u_rec): stride of this dimension's first node, in records
+    int64_t rec_stride;
 };
 
 // Experiment knobs (DIND_* environment variables; not part of the API).  Read from the environment ONCE per
@@ -147,6 +149,7 @@ struct Knobs {
     int c3_tile = -1;    // DIND_C3_TILE: points per work item of the tile kernels (0 = one-point kernels, -1 = default)
     bool no_lut = false, no_split = false, no_cells = false, no_aos = false, no_small = false, no_slice = false;
     bool persist = false;      // DIND_PERSIST=1: the persistent two-stage 4-D grid kernel instead of two launches
+    int rec = -1;        // DIND_REC: cell-record copy of u for multilinear tables at iid points (0 = never, 1 = always, -1 = by size)
 };
 
 template <typename T>
@@ -156,6 +159,7 @@ struct EvalParams {
     const T* u;            // (n_1..n_N, comps): NURBS: pre-multiplied by the weights
     const T* wts;          // NURBS weights (n_1..n_N) or null
     const T* u_aos;        // optional component-fastest copy of u: u_aos[c + n_comp * i] (unstructured, 2..4 components)
+    const T* u_rec;        // optional cell-record copy of u_aos (dind_fast_unstructured_rec.cu): all 2^N corners of a cell contiguous
     T* out;                // (n_points, comps)
     int64_t n_points;
     int64_t u_comp_stride;

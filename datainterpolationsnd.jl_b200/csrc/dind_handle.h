@@ -105,6 +105,8 @@ struct dind_interp_s {
     dind::DevBuf split_scratch;   // stage-1 results of the two-stage 4-D grid evaluation
     dind::DevBuf u_aos;       // component-fastest copy of u (vector-valued unstructured evaluation)
     bool u_aos_valid = false;
+    dind::DevBuf u_rec;       // cell-record copy of u_aos (multilinear tables larger than L2 at iid points)
+    bool u_rec_valid = false, u_rec_declined = false;   // declined: no room for it — do not ask again until the next dind_set_u
     // cell-sorted plan for eval_unstructured (dind_plan.cu)
     bool plan_valid = false;
     int64_t plan_n = 0;

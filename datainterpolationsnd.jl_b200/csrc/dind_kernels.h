@@ -50,6 +50,15 @@ template <typename T> bool aos_supported(const EvalParams<T>& P);
 template <typename T> bool try_eval_fast_unstructured_aos(const EvalParams<T>& P, cudaStream_t s, const char** name,
                                                           cudaError_t* err, int* launches);
 
+// Cell-record copy of u for multilinear tables larger than L2, evaluated at iid points (dind_fast_unstructured_rec.cu):
+// u_rec[cell(i_2..i_N)][i_1][corner(k_2..k_N)][component] — the 2^N corners of a point are one contiguous block.
+template <typename T> bool rec_supported(const EvalParams<T>& P);
+template <typename T> size_t rec_table_bytes(const EvalParams<T>& P);
+template <typename T> void rec_fill_strides(EvalParams<T>& P);
+template <typename T> cudaError_t launch_rec_build(const EvalParams<T>& P, T* u_rec, cudaStream_t s);   // from P.u_aos
+template <typename T> bool try_eval_fast_unstructured_rec(const EvalParams<T>& P, cudaStream_t s, const char** name,
+                                                          cudaError_t* err, int* launches);
+
 // Fused value + first partial derivatives (dind_fast_gradient.cu): out[(point, comp, slot)], slot 0 = value.
 template <typename T> bool try_eval_fast_gradient(const EvalParams<T>& P, cudaStream_t s, const char** name,
                                                   cudaError_t* err, int* launches);

@@ -688,6 +688,48 @@ def test_tile_kernel_variants_are_bit_identical(D, tile, shape, monkeypatch):
     ref_itp.close()
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n_in,n_comp", [(2, 2), (3, 3), (3, 4), (4, 2), (4, 4), (5, 4), (5, 2), (6, 3)])
+def test_cell_record_table_is_bit_identical(D, n_in, n_comp, dtype, monkeypatch):
+    """DIND_REC=1 forces the cell-record copy of u (dind_fast_unstructured_rec.cu: every point's 2^N corners in one
+    contiguous block; chosen by size for tables larger than L2, e.g. BASELINE config 5).  Same weights, same FMA order:
+    the bits of the plain gather, for values, a derivative and with the cached idx_eval, incl. non-finite and
+    out-of-span coordinates; and the oracle's values."""
+    rng = np.random.default_rng(4321 + 10 * n_in + n_comp)
+    # the kernel exists where a lane's share of a 128-byte line is whole nodes of one half-record
+    has_rec = n_in >= 3 and (1 << (n_in - 1)) * (4 if n_comp == 3 else n_comp) * np.dtype(dtype).itemsize >= 128
+    kinds, degrees = ("linear",) * n_in, (0,) * n_in
+    n_knots = tuple([5, 4, 3, 6, 2, 3][:n_in])           # a 2-knot axis: one cell
+    ts, u, _ = _case(rng, kinds, degrees, n_knots, (n_comp,), dtype)
+    xs = H.zipped_queries(rng, ts, 20000, dtype)
+    special = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, np.finfo(dtype).max], dtype=dtype)
+    xs = [np.concatenate([x, np.roll(special, d)]).astype(dtype) for d, x in enumerate(xs)]
+    mk = lambda: D.NDInterpolation(u, H.make_dims(D, kinds, ts, xs, degrees, None, max_deriv=[1] * n_in))
+    monkeypatch.setenv("DIND_REC", "0")
+    ref_itp = mk()
+    monkeypatch.setenv("DIND_REC", "1")
+    itp = mk()                                        # the knob is read once, in dind_create
+    monkeypatch.delenv("DIND_REC")
+    for o in (None, (0,) * (n_in - 1) + (1,), (1,) + (0,) * (n_in - 1)):
+        for flags in (0, 1):                          # 1 = DIND_FLAG_CACHED_IDX
+            ref = D.eval_unstructured(ref_itp, derivative_orders=o, flags=flags)
+            assert ref_itp.last_kernel.startswith("unstructured_aos"), ref_itp.last_kernel
+            got = D.eval_unstructured(itp, derivative_orders=o, flags=flags)
+            assert itp.last_kernel.startswith("unstructured_rec" if has_rec else "unstructured_aos"), itp.last_kernel
+            assert np.array_equal(ref, got, equal_nan=True), (o, flags)
+    # a new u rebuilds the table
+    u2 = (u * 0.5 + 1).astype(dtype)
+    itp.set_u(u2)
+    ref_itp.set_u(u2)
+    assert np.array_equal(D.eval_unstructured(ref_itp), D.eval_unstructured(itp), equal_nan=True)
+    assert itp.last_kernel.startswith("unstructured_rec" if has_rec else "unstructured_aos")
+    # the oracle's values (floatmax coordinates overflow to inf - inf in another order there: left to the bit comparison)
+    ok = np.all([np.abs(np.nan_to_num(x, nan=0.0, posinf=0.0, neginf=0.0)) < 1e30 for x in xs], axis=0)
+    H.assert_close(D.eval_unstructured(itp)[ok], H.oracle_eval(kinds, ts, u2, [x[ok] for x in xs], degrees=degrees), dtype)
+    itp.close()
+    ref_itp.close()
+
+
 def test_nurbs_weights_with_constant_axis(D):
     """BASELINE config 4 names NURBS weights with mixed Constant(left=true)/BSpline dimensions: no
     reference semantics — defined as the tensor product of the per-dimension stencils
