@@ -16,8 +16,8 @@
 // lines).  Size: prod(n_d - 1, d >= 2) * n_1 * 2^(N-1) nodes (config 5: 7.6 GB of the 180 GB), built once per
 // dind_set_u by one pass over the component-fastest copy.
 //
-// FOUR LANES evaluate one point: every load instruction of a quad covers one whole line of the block (lane q its
-// q-th 32 bytes).  The slots of a half-record are ordered so that what lane q receives is the sub-cube of axes
+// FOUR LANES gather and contract one point (the search and the weights were computed one point per lane and
+// arrive by shuffle): every load instruction of a quad covers one whole line of the block (lane q its q-th 32 bytes).  The slots of a half-record are ordered so that what lane q receives is the sub-cube of axes
 // 1..N-2 at (k_{N-1}, k_N) = q: the lane contracts those axes in registers, the last two axes are two
 // butterfly exchanges (shfl.xor 1, 2) after which every lane of the quad holds the result and lane c stores
 // component c.  The weights and the order of the FMAs are those of unstructured_aos_kernel (each partial sum is
@@ -128,6 +128,9 @@ __device__ __forceinline__ Vec<T, C> quad_axis(const Vec<T, C>& mine, const T (&
     return acc;
 }
 
+// A warp owns 32 consecutive points.  Phase A, one point per lane: interval search and weights of every dimension
+// (t_eval loads coalesced, no redundant work).  Phase B, four rounds: quad g gathers and contracts point 8r + g, whose
+// weights and record index arrive by shuffle from the lane that computed them.
 template <typename T, int N, int C>
 __global__ void __launch_bounds__(RBLOCK) unstructured_rec_kernel(const __grid_constant__ EvalParams<T> P) {
     constexpr int NPC = RecGeom<T, C>::NPC;
@@ -135,9 +138,9 @@ __global__ void __launch_bounds__(RBLOCK) unstructured_rec_kernel(const __grid_c
     constexpr int JJ = M / NPC;                // its chunks per half-record
     constexpr int HALF_BYTES = (1 << (N - 1)) * RecGeom<T, C>::NODE_BYTES;
     static_assert(JJ >= 1, "a lane's share of a line must be whole nodes of one half-record");
-    const int64_t t = (int64_t)blockIdx.x * RBLOCK + threadIdx.x;
-    const int q = (int)(t & 3);
-    const int64_t k = min(t >> 2, P.n_points - 1);   // whole quads stay alive for the exchanges
+    const int64_t k0 = (int64_t)blockIdx.x * RBLOCK + (threadIdx.x & ~31);   // the warp's first point
+    const int lane = threadIdx.x & 31, q = lane & 3;
+    const int64_t k = min(k0 + lane, P.n_points - 1);
     T w[N][2];
     int64_t rec = 0;
 #pragma unroll
@@ -147,20 +150,33 @@ __global__ void __launch_bounds__(RBLOCK) unstructured_rec_kernel(const __grid_c
         const int cached = P.use_cached_idx ? __ldcs(D.idx_eval + k) : 0;
         rec += (int64_t)linear_stencil<T>(D, x, cached, w[d]) * D.rec_stride;
     }
-    const char* base = reinterpret_cast<const char*>(P.u_rec) + rec * HALF_BYTES + q * 32;
-    Vec<T, C> nd[2][M];
+    const char* mine = reinterpret_cast<const char*>(P.u_rec) + rec * HALF_BYTES;
 #pragma unroll
-    for (int k1 = 0; k1 < 2; ++k1)
+    for (int r = 0; r < 4; ++r) {
+        const int src = 8 * r + (lane >> 2);
+        const char* base = reinterpret_cast<const char*>(__shfl_sync(0xffffffffu, (unsigned long long)mine, src)) + q * 32;
+        Vec<T, C> nd[2][M];
 #pragma unroll
-        for (int jj = 0; jj < JJ; ++jj) load_chunk<T, C>(base + k1 * HALF_BYTES + jj * 128, &nd[k1][jj * NPC]);
-    Vec<T, C> acc = QuadContract<T, N - 3, N, C, M, 0>::run(nd, w);
-    acc = quad_axis<T, C>(acc, w[N - 2], q, 0);
-    acc = quad_axis<T, C>(acc, w[N - 1], q, 1);
-    if ((t >> 2) >= P.n_points) return;
-    // lane c stores component c: a warp writes 8 consecutive points of every component column
+        for (int k1 = 0; k1 < 2; ++k1)
 #pragma unroll
-    for (int c = 0; c < C; ++c)
-        if (q == c) __stcs(P.out + (int64_t)c * P.out_comp_stride + k * P.out_point_stride, acc.v[c]);
+            for (int jj = 0; jj < JJ; ++jj) load_chunk<T, C>(base + k1 * HALF_BYTES + jj * 128, &nd[k1][jj * NPC]);
+        T wr[N][2];
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            wr[d][0] = __shfl_sync(0xffffffffu, w[d][0], src);
+            wr[d][1] = __shfl_sync(0xffffffffu, w[d][1], src);
+        }
+        Vec<T, C> acc = QuadContract<T, N - 3, N, C, M, 0>::run(nd, wr);
+        acc = quad_axis<T, C>(acc, wr[N - 2], q, 0);
+        acc = quad_axis<T, C>(acc, wr[N - 1], q, 1);
+        // lane c stores component c: a warp writes 8 consecutive points of every component column
+        const int64_t kp = k0 + src;
+        if (kp < P.n_points) {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (q == c) __stcs(P.out + (int64_t)c * P.out_comp_stride + kp * P.out_point_stride, acc.v[c]);
+        }
+    }
 }
 
 struct RecShape {
@@ -254,9 +270,7 @@ cudaError_t launch_rec_build(const EvalParams<T>& P, T* u_rec, cudaStream_t s) {
 template <typename T>
 bool try_eval_fast_unstructured_rec(const EvalParams<T>& P, cudaStream_t s, const char** name, cudaError_t* err, int* launches) {
     if (!P.u_rec || !rec_supported<T>(P)) return false;
-    const int64_t nb64 = (P.n_points * 4 + RBLOCK - 1) / RBLOCK;   // four lanes per point
-    if (nb64 >= (1LL << 31)) return false;
-    const unsigned nb = (unsigned)nb64;
+    const unsigned nb = (unsigned)((P.n_points + RBLOCK - 1) / RBLOCK);
     const int N = P.n_in, C = P.n_comp;
     constexpr int TB = (int)sizeof(T);
     *launches = 1;
