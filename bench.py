@@ -611,6 +611,16 @@ def bench_unstructured_family(D, torch, dist, wl, rank, world, local_rank, steps
             extra["roofline_fma"] = {"bound": "fp64 pipe", "peak_Gpoints_per_s_per_gpu": round(fma_bound, 1),
                                      "frac": round(n / (ms * 1e-3) / 1e9 / fma_bound, 4),
                                      "note": f"{ops} FP64 operations per point at the measured 17.6 T/s (DESIGN.md §6)"}
+        if wl.key == "c5" and mode == "iid":
+            # iid order: no two points share a cell, so every point must fetch its own 2^5 corner nodes (512 B) from a
+            # table that does not fit in L2 — the DRAM traffic that is necessary in this order (ncu: 523 B/point read)
+            need = n * (2 ** n_in * n_comp * esz + (n_in + n_comp) * esz)
+            gbs = need / (ms * 1e-3) / 1e9
+            hbm = measured_peaks()[0]["hbm_gbs"]
+            extra["roofline_gather"] = {"bound": "hbm, iid point order", "bytes_per_point": need // n, "achieved": round(gbs, 1),
+                                        "peak": hbm, "unit": "GB/s", "frac": round(gbs / hbm, 4),
+                                        "note": "cell-record copy of u (7.6 GB): one contiguous 512-byte block per point, requested as whole "
+                                                "128-byte lines by four lanes (dind_fast_unstructured_rec.cu)"}
         res[mode] = _entry(wl, ms, n_total, alg, per_step, kernel, extra)
         if mode.startswith("gradient"):
             del gout

@@ -131,8 +131,10 @@ __device__ __forceinline__ Vec<T, C> quad_axis(const Vec<T, C>& mine, const T (&
 // A warp owns 32 consecutive points.  Phase A, one point per lane: interval search and weights of every dimension
 // (t_eval loads coalesced, no redundant work).  Phase B, four rounds: quad g gathers and contracts point 8r + g, whose
 // weights and record index arrive by shuffle from the lane that computed them.
+// 4 CTAs/SM = 64 registers: ptxas then keeps a second round's loads in flight (config 5, 1e8 iid points: 12.2
+// Gpoints/s = 6.7 TB/s of record traffic; 52 registers without the bound 10.2, 5 / 6 CTAs per SM 10.7 / 10.6)
 template <typename T, int N, int C>
-__global__ void __launch_bounds__(RBLOCK) unstructured_rec_kernel(const __grid_constant__ EvalParams<T> P) {
+__global__ void __launch_bounds__(RBLOCK, 4) unstructured_rec_kernel(const __grid_constant__ EvalParams<T> P) {
     constexpr int NPC = RecGeom<T, C>::NPC;
     constexpr int M = 1 << (N - 3);            // the lane's nodes per i_1
     constexpr int JJ = M / NPC;                // its chunks per half-record
