@@ -647,6 +647,18 @@ def bench_unstructured_family(D, torch, dist, wl, rank, world, local_rank, steps
             "what": f"dind_allgather_out: {n_comp} ncclAllGather calls (one per component column) in one NCCL group, straight into the "
                     f"(n_total, {n_comp}) result; NVLink/NVSwitch bound"}
         fullbuf[0] = None
+        torch.cuda.empty_cache()
+        # the same work as ONE collective call: the shard is evaluated straight into its rows of the global array and the
+        # rows of the other ranks arrive chunk by chunk while the next chunk is computed (dind_eval_unstructured_allgather)
+        full2 = D.f_empty((n_total,) + shape[n_in:], wl.dtype, dev)
+        fn_f = lambda i: D.eval_unstructured_allgather_(full2, itp, n_total)
+        ms_f = _time_steps(torch, dist, stream, world, fn_f, max(2, min(steps, 5)), 2)
+        (ms_f,) = _max_over_ranks(torch, dist, world, dev, [ms_f])
+        res["iid"]["with_allgather_overlapped"] = {
+            "value": round(n_total / (ms_f * 1e-3) / 1e9, 3), "ms_per_step": round(ms_f, 3),
+            "what": "dind_eval_unstructured_allgather: no local output array; NCCL send/recv groups of chunk j on the communicator's "
+                    "stream under the kernel of chunk j + 1; bound by max(evaluation, exchange) instead of their sum"}
+        del full2
     itp.close()
     del xs, out, ud
     torch.cuda.empty_cache()

@@ -27,13 +27,13 @@ import numpy as np
 
 from . import _lib
 from ._lib import DindError, shard_range  # noqa: F401
-from .parallel import gather_grid, gather_unstructured, shard_t_eval  # noqa: F401
+from .parallel import eval_unstructured_allgather_, gather_grid, gather_unstructured, shard_t_eval  # noqa: F401
 
 __all__ = [
     "NDInterpolation", "LinearInterpolationDimension", "ConstantInterpolationDimension",
     "BSplineInterpolationDimension", "NURBSWeights", "EmptyCache", "eval_unstructured",
     "eval_unstructured_", "eval_grid", "eval_grid_", "DindError", "f_empty", "shard_range",
-    "shard_t_eval", "gather_unstructured", "gather_grid", "eval_unstructured_gradient",
+    "shard_t_eval", "gather_unstructured", "gather_grid", "eval_unstructured_allgather_", "eval_unstructured_gradient",
 ]
 
 

@@ -46,6 +46,7 @@ SYMBOLS = [
     ("dind_comm_destroy", _i, [_vp]),
     ("dind_comm_info", _i, [_vp, _pint, _pint, _pint]),
     ("dind_allgather_out", _i, [_vp, _vp, _vp, _i64, _i64, _i64, _u]),
+    ("dind_eval_unstructured_allgather", _i, [_vp, _vp, _i64, _pint, _i, _u]),
     ("dind_host_register", _i, [_vp, _i64]),
     ("dind_host_unregister", _i, [_vp]),
     ("dind_last_error", C.c_char_p, []),

@@ -346,7 +346,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     P.out = d_out;
     P.n_points = n_points;
     P.u_comp_stride = h->comp_stride;
-    P.out_comp_stride = n_points;
+    P.out_comp_stride = h->out_comp_stride_override ? h->out_comp_stride_override : n_points;
     P.out_point_stride = 1;
     P.n_comp = (int32_t)h->n_comp;
     P.n_in = N;
@@ -672,7 +672,29 @@ int eval_points(dind_interp_s* h, void* out, const void* const* t, int64_t n, co
     return run_eval<T>(h, out, orders, false, t_dev, n_eval, false, flags);
 }
 
+template <typename T>
+int eval_point_rows_t(dind_interp_s* h, void* out_rows, int64_t a, int64_t b, int64_t comp_stride, const int* orders_in) {
+    int orders[MAXN];
+    int rc = validate_orders(h, orders_in, true, orders);
+    if (rc) return rc;
+    const void* t_dev[MAXN];
+    int64_t n_eval[MAXN];
+    for (int d = 0; d < h->n_in; ++d) {
+        t_dev[d] = (const char*)h->dims[d].d_teval + (size_t)a * sizeof(T);
+        n_eval[d] = b - a;
+    }
+    h->out_comp_stride_override = comp_stride;
+    rc = run_eval<T>(h, out_rows, orders, false, t_dev, n_eval, false, DIND_FLAG_ASYNC);
+    h->out_comp_stride_override = 0;
+    return rc;
+}
+
 }  // namespace
+
+int dind::eval_point_rows(dind_interp_s* h, void* out_rows, int64_t a, int64_t b, int64_t comp_stride, const int* derivative_orders) {
+    return h->dtype == DIND_F32 ? eval_point_rows_t<float>(h, out_rows, a, b, comp_stride, derivative_orders)
+                                : eval_point_rows_t<double>(h, out_rows, a, b, comp_stride, derivative_orders);
+}
 
 // ============================================================================================
 extern "C" {

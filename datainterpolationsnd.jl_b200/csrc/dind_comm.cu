@@ -16,7 +16,9 @@
 // per (rank, column), since ncclAllGather needs equal counts.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <mutex>
+#include <vector>
 
 #include "dind_handle.h"
 
@@ -39,6 +41,8 @@ struct NcclApi {
     int (*GroupEnd)() = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     int (*GetVersion)(int*) = nullptr;
     std::string load_error;
@@ -71,6 +75,8 @@ static NcclApi& nccl() {
         api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
         api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
         api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+        api.Send = (decltype(api.Send))sym("ncclSend");
+        api.Recv = (decltype(api.Recv))sym("ncclRecv");
         api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
         api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
         if (!ok) { dlclose(api.lib); api.lib = nullptr; }
@@ -94,10 +100,20 @@ static int need_nccl() {
 struct CommState {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    // dind_eval_unstructured_allgather: the exchanges run on their own stream, ordered against the handle's stream by events
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> chunk_ready;
+    cudaEvent_t done = nullptr;
 };
 
 void comm_release(dind_interp_s* h) {
     if (h->comm) {
+        if (h->comm->stream) {
+            cudaStreamSynchronize(h->comm->stream);
+            cudaStreamDestroy(h->comm->stream);
+        }
+        for (cudaEvent_t e : h->comm->chunk_ready) cudaEventDestroy(e);
+        if (h->comm->done) cudaEventDestroy(h->comm->done);
         if (h->comm->comm) nccl().CommDestroy(h->comm->comm);
         delete h->comm;
         h->comm = nullptr;
@@ -205,6 +221,83 @@ int dind_allgather_out(dind_handle_t h, const void* out_local, void* out_global,
         if (r != ncclSuccess) return fail(DIND_ERR_NCCL, "NCCL all-gather of outputs failed: %s", N.GetErrorString(r));
         NCCL_TRY(rg);
         h->launches += 1;
+    }
+    if (!(flags & DIND_FLAG_ASYNC)) CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return DIND_OK;
+}
+
+int dind_eval_unstructured_allgather(dind_handle_t h, void* out_global, int64_t n_total, const int* derivative_orders,
+                                     int n_chunks, unsigned flags) {
+    if (!h) return fail(DIND_ERR_INVALID_ARGUMENT, "null handle");
+    if (n_total < 0) return fail(DIND_ERR_INVALID_ARGUMENT, "n_total must be non-negative");
+    if (!out_global) return fail(DIND_ERR_INVALID_ARGUMENT, "out_global is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, out_global) != cudaSuccess || a.type != cudaMemoryTypeDevice) {
+            cudaGetLastError();
+            return fail(DIND_ERR_INVALID_ARGUMENT, "out_global must be a device array");
+        }
+    }
+    CommState* cs = h->comm;
+    const int world = cs ? cs->world : 1, rank = cs ? cs->rank : 0;
+    int64_t lo = 0, hi = 0;
+    dind_shard_range(n_total, rank, world, &lo, &hi);
+    for (int d = 0; d < h->n_in; ++d) {
+        if (!h->dims[d].teval_set) return fail(DIND_ERR_STATE, "t_eval of dimension %d has not been set (dind_set_t_eval)", d + 1);
+        if (h->dims[d].n_eval != hi - lo)
+            return fail(DIND_ERR_SIZE_MISMATCH, "rank %d of %d owns %lld of %lld points, t_eval of dimension %d has %lld",
+                        rank, world, (long long)(hi - lo), (long long)n_total, d + 1, (long long)h->dims[d].n_eval);
+    }
+    // one-time work (component-fastest / cell-record copies of u) is sized by the whole shard, not by a chunk
+    int rc = dind_build_caches(h, 0, derivative_orders, DIND_FLAG_ASYNC);
+    if (rc) return rc;
+    const size_t esz = h->esz;
+    const int64_t n_comp = h->n_comp;
+    char* dst = (char*)out_global;
+    const int64_t per_rank = (n_total + world - 1) / std::max(world, 1);
+    int K = n_chunks > 0 ? n_chunks : (int)std::min<int64_t>(16, std::max<int64_t>(1, per_rank / 2000000));
+    if (world == 1) K = 1;
+    K = std::min(K, 64);
+    if (world > 1) {
+        if (!cs->stream) CUDA_TRY(cudaStreamCreateWithFlags(&cs->stream, cudaStreamNonBlocking));
+        if (!cs->done) CUDA_TRY(cudaEventCreateWithFlags(&cs->done, cudaEventDisableTiming));
+        while ((int)cs->chunk_ready.size() < K) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            cs->chunk_ready.push_back(e);
+        }
+    }
+    auto cut = [K](int64_t n, int j) { return (int64_t)((__int128)n * j / K); };   // chunk j of a shard of n rows: [cut(j), cut(j + 1))
+    NcclApi& N = nccl();
+    const int dt = h->dtype == DIND_F32 ? ncclFloat32 : ncclFloat64;
+    for (int j = 0; j < K; ++j) {
+        const int64_t a = cut(hi - lo, j), b = cut(hi - lo, j + 1);
+        if (b > a && (rc = eval_point_rows(h, dst + (size_t)(lo + a) * esz, a, b, n_total, derivative_orders))) return rc;
+        if (world == 1) continue;
+        CUDA_TRY(cudaEventRecord(cs->chunk_ready[j], h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(cs->stream, cs->chunk_ready[j], 0));
+        NCCL_TRY(N.GroupStart());
+        int r = ncclSuccess;
+        for (int step = 1; step < world && r == ncclSuccess; ++step) {
+            const int to = (rank + step) % world, from = (rank - step + world) % world;
+            int64_t flo, fhi;
+            dind_shard_range(n_total, from, world, &flo, &fhi);
+            const int64_t fa = cut(fhi - flo, j), fb = cut(fhi - flo, j + 1);
+            for (int64_t c = 0; c < n_comp && r == ncclSuccess; ++c) {
+                if (b > a) r = N.Send(dst + ((size_t)c * n_total + lo + a) * esz, (size_t)(b - a), dt, to, cs->comm, cs->stream);
+                if (fb > fa && r == ncclSuccess)
+                    r = N.Recv(dst + ((size_t)c * n_total + flo + fa) * esz, (size_t)(fb - fa), dt, from, cs->comm, cs->stream);
+            }
+        }
+        const int rg = N.GroupEnd();
+        if (r != ncclSuccess) return fail(DIND_ERR_NCCL, "NCCL exchange of output rows failed: %s", N.GetErrorString(r));
+        NCCL_TRY(rg);
+        h->launches += 1;
+    }
+    if (world > 1) {
+        CUDA_TRY(cudaEventRecord(cs->done, cs->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, cs->done, 0));   // whatever follows on the handle's stream sees the global output
     }
     if (!(flags & DIND_FLAG_ASYNC)) CUDA_TRY(cudaStreamSynchronize(h->stream));
     return DIND_OK;

@@ -81,6 +81,10 @@ struct DimState {
 
 struct CommState;   // dind_comm.cu
 
+// dind_api.cu, for dind_comm.cu: unstructured evaluation of the cached points [a, b) of this handle into rows that are
+// `comp_stride` elements apart per output component (out_rows = address of row a of component 0); queued, not waited for
+int eval_point_rows(dind_interp_s* h, void* out_rows, int64_t a, int64_t b, int64_t comp_stride, const int* derivative_orders);
+
 }  // namespace dind
 
 struct dind_interp_s {
@@ -135,6 +139,7 @@ struct dind_interp_s {
     cudaEvent_t ev_kernel = nullptr, ev_d2h[2] = {nullptr, nullptr};
     dind::DevBuf pts_stage[dind::MAXN];
     void* small_host = nullptr;     // pinned, device-mapped staging of the small-batch (latency) path of dind_eval_points
+    int64_t out_comp_stride_override = 0;   // != 0: component columns of `out` are this many elements apart (eval_point_rows)
     std::string last_kernel = "none";
     int64_t launches = 0;
     dind::CommState* comm = nullptr;   // NCCL communicator of dind_comm_init (dind_comm.cu), null = single GPU

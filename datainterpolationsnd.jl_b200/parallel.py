@@ -135,6 +135,32 @@ def _gather_device(out_local, lead_shape, n_total, unit, group, interp):
     return full
 
 
+def eval_unstructured_allgather_(out_global, interp, n_total, *, derivative_orders=None, n_chunks=0, group=None):
+    """Point-sharded eval_unstructured! + all-gather in one collective call (dind_eval_unstructured_allgather): `interp`
+    holds this rank's shard of the points (shard_t_eval), the shard is evaluated straight into its rows of the global
+    (n_total, out...) column-major CUDA tensor `out_global`, and the other ranks' rows arrive by NCCL while the next
+    chunk of the shard is still being computed.  No local output array.  Returns out_global."""
+    import ctypes as C
+
+    import torch
+
+    from . import _is_f_contiguous_torch, _lib, _orders
+    if not (_is_cuda_tensor(out_global) and _is_f_contiguous_torch(out_global)):
+        raise _lib.DindError(_lib.ERR_INVALID_ARGUMENT, "out_global must be a column-major CUDA tensor (see f_empty)")
+    want = (int(n_total),) + tuple(interp.output_size)
+    if tuple(out_global.shape) != want:
+        raise _lib.DindError(_lib.ERR_SIZE_MISMATCH, f"out_global has shape {tuple(out_global.shape)}, expected {want}")
+    h = interp._h
+    _, world = rank_world(group)
+    if world > 1 and not getattr(h, "_comm_ready", False):
+        init_comm(h, group)
+        h._comm_ready = True
+    h.set_stream(torch.cuda.current_stream(out_global.device).cuda_stream)
+    _lib.check(h.lib.dind_eval_unstructured_allgather(h.h, C.c_void_p(out_global.data_ptr()), int(n_total),
+                                                      _orders(derivative_orders, interp.N_in), int(n_chunks), _lib.FLAG_ASYNC))
+    return out_global
+
+
 def _gather_rows(rows_local, counts, unit, group):
     """gloo / CPU path (tests): rank r broadcasts its (C, count_r * unit) block into a scratch of that size, which
     is copied into the final (C, total * unit) buffer — the global output is held once."""

@@ -217,6 +217,20 @@ int dind_comm_info(dind_handle_t handle, int* rank, int* world, int* nccl_versio
 int dind_allgather_out(dind_handle_t handle, const void* out_local, void* out_global, int64_t n_total, int64_t unit,
                        int64_t n_comp, unsigned flags);
 
+/* Collective: dind_eval_unstructured of this rank's shard, written straight into its final rows of the GLOBAL output,
+ * plus the all-gather of the other ranks' rows — the exchange of chunk j runs (NCCL point-to-point calls of one group,
+ * on the communicator's own stream) while the kernel of chunk j + 1 computes, so the gather costs what exceeds the
+ * evaluation instead of adding to it.  Still "after the kernels, never inside them" (north star (5)): a chunk is
+ * exchanged when the kernel that produced it has finished.
+ *   out_global: DEVICE array (n_total, out...) column-major, the same on every rank when the call returns;
+ *   the handle's t_eval (dind_set_t_eval) holds the rank's shard: n_eval = hi - lo of dind_shard_range(n_total, rank, world);
+ *   n_chunks <= 0: chosen from n_total / world (the same value on every rank).
+ * No local output array, no staging: a GPU holds the global output exactly once.  Uneven shards need nothing special
+ * (every message carries its own count).  Without a communicator (world = 1) this is dind_eval_unstructured into out_global.
+ * The reference has no multi-device path (src/interpolation_parallel.jl:34-52 evaluates on ONE backend). */
+int dind_eval_unstructured_allgather(dind_handle_t handle, void* out_global, int64_t n_total, const int* derivative_orders,
+                                     int n_chunks, unsigned flags);
+
 /* ---- pinned host memory (for the host-buffer path) ---------------------------------------- */
 int dind_host_register(void* ptr, int64_t bytes);
 int dind_host_unregister(void* ptr);

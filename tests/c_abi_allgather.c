@@ -75,6 +75,20 @@ static int run(int rank, int world, dind_handle_t h, int64_t n_total) {
             bad = 1;
         }
     }
+    /* the same result from ONE collective call: the shard is evaluated straight into its rows of the global array and
+     * the rows of the other ranks arrive chunk by chunk while the next chunk is computed (3 chunks here) */
+    double* d_fused = NULL;
+    CU(cudaMalloc((void**)&d_fused, sizeof(double) * (size_t)(2 * n_total + 1)));
+    CU(cudaMemset(d_fused, 0xff, sizeof(double) * (size_t)(2 * n_total + 1)));
+    CHECK(dind_eval_unstructured_allgather(h, d_fused, n_total, NULL, 3, 0));
+    double* g2 = (double*)malloc(sizeof(double) * (size_t)(2 * n_total + 1));
+    CU(cudaMemcpy(g2, d_fused, sizeof(double) * (size_t)(2 * n_total), cudaMemcpyDeviceToHost));
+    if (!bad && memcmp(g, g2, sizeof(double) * (size_t)(2 * n_total))) {
+        fprintf(stderr, "[rank %d] n_total=%lld: dind_eval_unstructured_allgather differs from eval + allgather\n", rank, (long long)n_total);
+        bad = 1;
+    }
+    free(g2);
+    cudaFree(d_fused);
     free(g); free(x1); free(x2);
     cudaFree(d_local); cudaFree(d_global);
     return bad ? 2 : 0;

@@ -8,6 +8,8 @@ and the outputs are all-gathered by dind_allgather_out (NCCL inside libdind.so).
   * plan-sorted == unsorted, bit for bit;
   * gather == concatenation of the shards: own segment bit-identical, every other segment through an exact
     integer checksum exchanged between the ranks;
+  * the one-call form (dind_eval_unstructured_allgather: shard evaluated into its rows of the global array, rows
+    exchanged chunk by chunk under the next chunk's kernel) gives the same global array;
   * a slab-sharded eval_grid (3-D trilinear) gathers to the single-GPU grid, bit for bit.
 
     python -m torch.distributed.run --nproc-per-node N tests/multi_gpu_worker.py [--n-total 4000000000] [--no-gather]
@@ -91,6 +93,42 @@ def main():
         D.eval_unstructured_(out_s, itp, flags=CELL_SORTED)
         assert torch.equal(out_s, out)
         del out_s
+    # exact checksum of every rank's shard (all ranks'), for the gathered arrays below
+    def checksum(t):
+        return t.contiguous().view(torch.int32).to(torch.int64).sum(dim=0)
+    mine = torch.stack([checksum(out[:, c]) for c in range(4)])
+    sums = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(sums, mine)
+
+    def check_gathered(full, what):
+        assert tuple(full.shape) == (n_total, 4)
+        assert torch.equal(full[lo:hi], out), what
+        for r in range(world):
+            rlo, rhi = D.shard_range(n_total, r, world)
+            seg = torch.stack([checksum(full[rlo:rhi, c]) for c in range(4)])
+            assert torch.equal(seg, sums[r]), f"{what}: segment of rank {r} differs"
+
+    # --- evaluation + all-gather as ONE collective call (dind_eval_unstructured_allgather): the shard goes straight into
+    #     its rows of the global array, the other ranks' rows arrive while the next chunk is computed
+    fused_ms = None
+    if not args.no_gather:
+        full2 = D.f_empty((n_total, 4), np.float32, dev)
+        D.eval_unstructured_allgather_(full2, itp, n_total)      # warm-up: communicator, stream, events
+        torch.cuda.synchronize()
+        full2.fill_(float("nan"))
+        dist.barrier()
+        ev[2].record()
+        D.eval_unstructured_allgather_(full2, itp, n_total)
+        ev[3].record()
+        torch.cuda.synchronize()
+        fused_ms = ev[2].elapsed_time(ev[3])
+        check_gathered(full2, "eval_unstructured_allgather")
+        full2.fill_(float("nan"))
+        D.eval_unstructured_allgather_(full2, itp, n_total, n_chunks=7)     # chunk boundaries that do not divide the shard
+        torch.cuda.synchronize()
+        check_gathered(full2, "eval_unstructured_allgather, 7 chunks")
+        del full2
+        torch.cuda.empty_cache()
     itp.close()
     del xs_d
     torch.cuda.empty_cache()
@@ -106,18 +144,7 @@ def main():
         ev[3].record()
         torch.cuda.synchronize()
         gather_ms = ev[2].elapsed_time(ev[3])
-        assert tuple(full.shape) == (n_total, 4)
-        assert torch.equal(full[lo:hi], out)
-        # exact checksum of every rank's shard, exchanged, against the matching segment of the gathered array
-        def checksum(t):
-            return t.contiguous().view(torch.int32).to(torch.int64).sum(dim=0)
-        mine = torch.stack([checksum(out[:, c]) for c in range(4)])
-        sums = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(sums, mine)
-        for r in range(world):
-            rlo, rhi = D.shard_range(n_total, r, world)
-            seg = torch.stack([checksum(full[rlo:rhi, c]) for c in range(4)])
-            assert torch.equal(seg, sums[r]), f"gathered segment of rank {r} differs"
+        check_gathered(full, "dind_allgather_out")
         recv = (n_total - n_local) * 16
         busbw = recv / (gather_ms * 1e-3) / 1e9
         del full
@@ -145,13 +172,15 @@ def main():
     itg.close()
     whole.close()
 
-    stats = torch.tensor([eval_ms, gather_ms or 0.0, err], device=dev, dtype=torch.float64)
+    stats = torch.tensor([eval_ms, gather_ms or 0.0, err, fused_ms or 0.0], device=dev, dtype=torch.float64)
     dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     if rank == 0:
         rep = {"world": world, "n_total": n_total, "points_per_gpu": n_local, "eval_ms_max": round(float(stats[0]), 3),
                "eval_Gpoints_per_s": round(n_total / (float(stats[0]) * 1e-3) / 1e9, 3),
                "allgather_ms_max": round(float(stats[1]), 3) if gather_ms else None,
                "allgather_busbw_GBps": round((n_total - n_local) * 16 / (float(stats[1]) * 1e-3) / 1e9, 1) if gather_ms else None,
+               "eval_plus_allgather_fused_ms_max": round(float(stats[3]), 3) if fused_ms else None,
+               "eval_plus_allgather_fused_Gpoints_per_s": round(n_total / (float(stats[3]) * 1e-3) / 1e9, 3) if fused_ms else None,
                "oracle_subsample_max_rel_err": float(f"{float(stats[2]):.3e}"), "ok": True}
         print("MULTI_GPU_REPORT " + json.dumps(rep), flush=True)
         if args.report:
