@@ -65,6 +65,8 @@ Knobs read_knobs() {
     k.no_slice = getenv("DIND_NO_SLICE") != nullptr;
     k.persist = getenv("DIND_PERSIST") != nullptr;
     k.rec = geti("DIND_REC", -1);
+    k.no_plan_recs = getenv("DIND_NO_PLAN_RECS") != nullptr;
+    k.plan_buckets = geti("DIND_PLAN_BUCKETS", -1);
     return k;
 }
 
@@ -363,6 +365,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     }
 
     int unperm_ct = 0, unperm_stride = 0;   // != 0: results are staged component-fastest and brought home after the kernel
+    bool use_buckets = false;
     if (!grid && have_idx_cache && (flags & DIND_FLAG_CELL_SORTED)) {
         if (n_points >= (1LL << 32) || h->comp_stride >= (1LL << 32))
             return fail(DIND_ERR_UNSUPPORTED, "DIND_FLAG_CELL_SORTED needs fewer than 2^32 points and u elements per component");
@@ -390,13 +393,20 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
                 ts[d] = (T*)h->plan_t[d].p;
             }
             size_t scratch_bytes = 0;
-            CUDA_TRY(plan_sort_points<T>(P, nullptr, ts, cells, cell_bits, nullptr, &scratch_bytes, h->stream));
+            CUDA_TRY(plan_sort_points<T>(P, nullptr, ts, cells, cell_bits, nullptr, &scratch_bytes, nullptr, h->stream));
             // sort scratch (keys in/out, values in, CUB temp) stays with the handle: a new t_eval of the same
             // size re-plans without cudaMalloc / cudaFree (which would also synchronise the device)
             size_t sb2 = 0;   // the un-permutation schedule sorts in the same scratch later
             CUDA_TRY(plan_bucket_schedule(nullptr, nullptr, nullptr, n_points, nullptr, &sb2, h->stream));
             CUDA_TRY(h->plan_scratch.ensure(std::max(scratch_bytes, sb2)));
-            CUDA_TRY(plan_sort_points<T>(P, (uint32_t*)h->plan_perm.p, ts, cells, cell_bits, h->plan_scratch.p, &scratch_bytes, h->stream));
+            // coordinate records for the one-read-per-point gather of the sorted t_eval: in the staging buffer of the
+            // un-permutation (free at this point); without room for them the gathers run per dimension
+            T* recs = nullptr;
+            if (!h->knobs.no_plan_recs) {
+                if (h->plan_stage.ensure((size_t)n_points * plan_rec_elems<T>(N) * sizeof(T)) == cudaSuccess) recs = (T*)h->plan_stage.p;
+                else (void)cudaGetLastError();
+            }
+            CUDA_TRY(plan_sort_points<T>(P, (uint32_t*)h->plan_perm.p, ts, cells, cell_bits, h->plan_scratch.p, &scratch_bytes, recs, h->stream));
             h->launches += 2 + N;
             h->plan_valid = true;
             h->plan_items[0].valid = h->plan_items[1].valid = false;
@@ -425,7 +435,14 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
             unperm_ct = ct;
             P.out_point_stride = unperm_stride;
             P.staged_records = 1;
-            {
+            // Where the record lands.  Records of less than a 32-byte sector: slots ordered by (destination window,
+            // plan position) — every window's region then fills front to back while the kernel sweeps the plan, so
+            // the records that share a sector (and a line) meet in L2 before it is written back (config 5, 16-byte
+            // records: 3.2 ms vs 5.4 ms with the records at their original index).  Whole-sector records go straight
+            // to staged[original index]: no second sort, no slot / destination arrays, and the copy home is a plain
+            // coalesced transpose (config 3: plan 18.8 -> 9.1 ms, fused gradient 13.1 -> 11.9 ms, values 4.52 -> 4.60 ms).
+            use_buckets = h->knobs.plan_buckets >= 0 ? h->knobs.plan_buckets != 0 : unperm_stride * (int)sizeof(T) < 32;
+            if (use_buckets) {
                 if (!h->plan_buckets_valid) {
                     CUDA_TRY(h->plan_slot2.ensure((size_t)n_points * sizeof(uint32_t)));
                     CUDA_TRY(h->plan_dest2.ensure((size_t)n_points * sizeof(uint32_t)));
@@ -576,7 +593,10 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     h->last_kernel = name;
     h->launches += nlaunch;
     if (unperm_ct) {
-        CUDA_TRY(plan_unbucket<T>((const T*)h->plan_stage.p, (const uint32_t*)h->plan_dest2.p, d_out, n_points, unperm_ct, unperm_stride, h->stream));
+        if (use_buckets)
+            CUDA_TRY(plan_unbucket<T>((const T*)h->plan_stage.p, (const uint32_t*)h->plan_dest2.p, d_out, n_points, unperm_ct, unperm_stride, h->stream));
+        else
+            CUDA_TRY(plan_unstage<T>((const T*)h->plan_stage.p, d_out, n_points, unperm_ct, unperm_stride, h->stream));
         h->launches += 1;
     }
     if (pipelined) {

@@ -24,9 +24,12 @@ template <typename T> cudaError_t launch_eval_generic(const EvalParams<T>& P, bo
 // memory order), t_sorted[d] = t_eval[d][perm].  cells != nullptr: the sort key is the packed per-dimension
 // first nodes (DimParams::cell_shift, cell_bits bits in all) and the sorted keys are kept in cells[].
 // scratch_bytes in/out: pass *scratch = nullptr to query the scratch size.
+// recs (optional, n_points * plan_rec_elems(n_in) elements, 32-byte aligned): room for one coordinate record per point;
+// with it the sorted copies of t_eval cost one random read per point instead of one per point and dimension.
+template <typename T> int plan_rec_elems(int n_in);
 template <typename T>
 cudaError_t plan_sort_points(const EvalParams<T>& P, uint32_t* perm, T* const* t_sorted, uint32_t* cells, int cell_bits,
-                             void* scratch, size_t* scratch_bytes, cudaStream_t s);
+                             void* scratch, size_t* scratch_bytes, T* recs, cudaStream_t s);
 
 // Work items over the sorted cell words (dind_plan.cu): the plan positions k whose distance from the start of their
 // run of equal cells is a multiple of `pts` — every item is <= pts consecutive points of one cell.  Two calls:
@@ -74,6 +77,9 @@ template <typename T> cudaError_t launch_grid_split(const EvalParams<T>& P, void
 cudaError_t plan_bucket_schedule(const uint32_t* perm, uint32_t* slot2, uint32_t* dest2, int64_t n, void* scratch,
                                  size_t* scratch_bytes, cudaStream_t s);
 constexpr int PLAN_WINDOW_SHIFT = 11;   // windows of 2048 original points
+// Un-permutation through a staging buffer in ORIGINAL order: the kernel wrote the record of plan position k to
+// staged[perm[k]]; this copies record j to out[j + c * n], reads and writes coalesced.
+template <typename T> cudaError_t plan_unstage(const T* staged, T* out, int64_t n, int ct, int rec_stride, cudaStream_t s);
 template <typename T> cudaError_t plan_unbucket(const T* staged, const uint32_t* dest2, T* out, int64_t n, int ct, int rec_stride, cudaStream_t s);
 
 // Specialised kernels.  Return true when they handled the evaluation (err holds the launch

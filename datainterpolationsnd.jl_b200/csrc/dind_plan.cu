@@ -29,20 +29,54 @@ constexpr int BLOCK = 256;
 // PACKED: the key is the per-dimension first nodes in bit fields (last dimension most significant: the same
 // order as the offset in u) — kept after the sort as the plan's cell words, which the evaluation kernels decode
 // instead of searching again.
+// recs != nullptr: the coordinates of point k are also written as one record of rec_elems elements (a multiple of
+// 32 bytes), so that the sorted copies of t_eval can be produced by ONE random read per point (plan_gather_rec_kernel)
+// instead of one per point and dimension: a random 4- or 8-byte read costs a whole L1 miss slot (config 5, 1e8 points:
+// five gathers of 1.77 ms each).
 template <typename T, bool PACKED>
 __global__ void __launch_bounds__(BLOCK) plan_key_kernel(const __grid_constant__ EvalParams<T> P, uint32_t* __restrict__ keys,
-                                                         uint32_t* __restrict__ vals) {
+                                                         uint32_t* __restrict__ vals, T* __restrict__ recs, int rec_elems) {
     const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (k >= P.n_points) return;
     int64_t base = 0;
     for (int d = 0; d < P.n_in; ++d) {
         const DimParams<T>& D = P.dim[d];
-        const int i0 = dim_first_node<T>(D, __ldcs(D.t_eval + k));
+        const T x = __ldcs(D.t_eval + k);
+        if (recs) recs[k * rec_elems + d] = x;
+        const int i0 = dim_first_node<T>(D, x);
         if (PACKED) base |= (int64_t)i0 << D.cell_shift;
         else base += (int64_t)i0 * D.u_stride;
     }
     keys[k] = (uint32_t)base;
     vals[k] = (uint32_t)k;
+}
+
+struct GatherDst {
+    void* p[MAXN];
+};
+// t_sorted[d][k] = recs[perm[k]][d]: the record is read with 32-byte loads, the N_in output streams are coalesced
+template <typename T, int N>
+__global__ void __launch_bounds__(BLOCK) plan_gather_rec_kernel(const T* __restrict__ recs, const uint32_t* __restrict__ perm,
+                                                                const GatherDst dst, int64_t n) {
+    constexpr int PER = 32 / (int)sizeof(T);            // elements per 32-byte load
+    constexpr int NL = (N + PER - 1) / PER;
+    const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (k >= n) return;
+    const T* r = recs + (int64_t)__ldcs(perm + k) * (NL * PER);
+    T v[NL * PER];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+        if constexpr (sizeof(T) == 4) {
+            asm("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                : "=f"(v[j * 8]), "=f"(v[j * 8 + 1]), "=f"(v[j * 8 + 2]), "=f"(v[j * 8 + 3]), "=f"(v[j * 8 + 4]), "=f"(v[j * 8 + 5]),
+                  "=f"(v[j * 8 + 6]), "=f"(v[j * 8 + 7]) : "l"(r + j * 8));
+        } else {
+            asm("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];"
+                : "=d"(v[j * 4]), "=d"(v[j * 4 + 1]), "=d"(v[j * 4 + 2]), "=d"(v[j * 4 + 3]) : "l"(r + j * 4));
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < N; ++d) __stcs((T*)dst.p[d] + k, v[d]);
 }
 
 template <typename T>
@@ -217,6 +251,74 @@ cudaError_t plan_bucket_schedule(const uint32_t* perm, uint32_t* slot2, uint32_t
     return cudaGetLastError();
 }
 
+// ---- un-permutation through a staging buffer in ORIGINAL order ---------------------------------------------------
+// The evaluation kernel writes the result of plan position k as one aligned record to staged[perm[k]] (one random,
+// whole-sector store per point — the same write pattern as the window-ordered slots above, without the second sort
+// and its two index arrays); this pass reads the records in order and writes the component columns, both coalesced.
+constexpr int UNS_BLOCK = 256;
+template <typename T, int BYTES>
+__global__ void __launch_bounds__(UNS_BLOCK) plan_unstage_vec_kernel(const T* __restrict__ staged, T* __restrict__ out, int64_t n, int ct) {
+    const int64_t j = (int64_t)blockIdx.x * UNS_BLOCK + threadIdx.x;
+    if (j >= n) return;
+    constexpr int E = BYTES / (int)sizeof(T);
+    T v[E];
+    if constexpr (BYTES == 32) {
+        const double2 a = __ldcs(reinterpret_cast<const double2*>(staged + j * E));
+        const double2 b = __ldcs(reinterpret_cast<const double2*>(staged + j * E) + 1);
+        memcpy(v, &a, 16);
+        memcpy(reinterpret_cast<char*>(v) + 16, &b, 16);
+    } else if constexpr (BYTES == 16) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(staged + j * E));
+        memcpy(v, &a, 16);
+    } else {
+        const float2 a = __ldcs(reinterpret_cast<const float2*>(staged + j * E));
+        memcpy(v, &a, 8);
+    }
+#pragma unroll
+    for (int c = 0; c < E; ++c)
+        if (c < ct) __stcs(out + j + (int64_t)c * n, v[c]);
+}
+// records of any size: a CTA's records are contiguous — coalesced copy to shared memory (row stride + 1: no bank
+// conflicts in the column reads), then one coalesced store stream per component
+template <typename T>
+__global__ void __launch_bounds__(UNS_BLOCK) plan_unstage_smem_kernel(const T* __restrict__ staged, T* __restrict__ out, int64_t n, int ct,
+                                                                     int stride) {
+    extern __shared__ __align__(16) unsigned char uns_smem[];
+    T* sm = reinterpret_cast<T*>(uns_smem);
+    const int64_t j0 = (int64_t)blockIdx.x * UNS_BLOCK;
+    const int np = (int)(n - j0 < UNS_BLOCK ? n - j0 : UNS_BLOCK);
+    const T* src = staged + j0 * stride;
+    for (int g = threadIdx.x; g < np * stride; g += UNS_BLOCK) {
+        const int r = g / stride;
+        sm[r * (stride + 1) + (g - r * stride)] = __ldcs(src + g);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < np)
+        for (int c = 0; c < ct; ++c) __stcs(out + j0 + threadIdx.x + (int64_t)c * n, sm[threadIdx.x * (stride + 1) + c]);
+}
+template <typename T>
+__global__ void __launch_bounds__(UNS_BLOCK) plan_unstage_loop_kernel(const T* __restrict__ staged, T* __restrict__ out, int64_t n, int ct,
+                                                                     int stride) {
+    const int64_t j = (int64_t)blockIdx.x * UNS_BLOCK + threadIdx.x;
+    if (j >= n) return;
+    for (int c = 0; c < ct; ++c) __stcs(out + j + (int64_t)c * n, __ldg(staged + j * stride + c));
+}
+
+template <typename T>
+cudaError_t plan_unstage(const T* staged, T* out, int64_t n, int ct, int rec_stride, cudaStream_t s) {
+    const unsigned nb = (unsigned)((n + UNS_BLOCK - 1) / UNS_BLOCK);
+    const int bytes = rec_stride * (int)sizeof(T);
+    const size_t smem = (size_t)UNS_BLOCK * (rec_stride + 1) * sizeof(T);
+    if (bytes == 32) plan_unstage_vec_kernel<T, 32><<<nb, UNS_BLOCK, 0, s>>>(staged, out, n, ct);
+    else if (bytes == 16) plan_unstage_vec_kernel<T, 16><<<nb, UNS_BLOCK, 0, s>>>(staged, out, n, ct);
+    else if (bytes == 8) plan_unstage_vec_kernel<T, 8><<<nb, UNS_BLOCK, 0, s>>>(staged, out, n, ct);
+    else if (smem <= 48 * 1024) plan_unstage_smem_kernel<T><<<nb, UNS_BLOCK, smem, s>>>(staged, out, n, ct, rec_stride);
+    else plan_unstage_loop_kernel<T><<<nb, UNS_BLOCK, 0, s>>>(staged, out, n, ct, rec_stride);
+    return cudaGetLastError();
+}
+template cudaError_t plan_unstage<float>(const float*, float*, int64_t, int, int, cudaStream_t);
+template cudaError_t plan_unstage<double>(const double*, double*, int64_t, int, int, cudaStream_t);
+
 template <typename T>
 cudaError_t plan_unbucket(const T* staged, const uint32_t* dest2, T* out, int64_t n, int ct, int rec_stride, cudaStream_t s) {
     const int cg_max = (96 * 1024) / (UNB_W * (int)sizeof(T));   // components per round: <= 96 KB of shared memory
@@ -232,8 +334,16 @@ template cudaError_t plan_unbucket<float>(const float*, const uint32_t*, float*,
 template cudaError_t plan_unbucket<double>(const double*, const uint32_t*, double*, int64_t, int, int, cudaStream_t);
 
 template <typename T>
+int plan_rec_elems(int n_in) {
+    const int per = 32 / (int)sizeof(T);
+    return (n_in + per - 1) / per * per;
+}
+template int plan_rec_elems<float>(int);
+template int plan_rec_elems<double>(int);
+
+template <typename T>
 cudaError_t plan_sort_points(const EvalParams<T>& P, uint32_t* perm, T* const* t_sorted, uint32_t* cells, int cell_bits,
-                             void* scratch, size_t* scratch_bytes, cudaStream_t s) {
+                             void* scratch, size_t* scratch_bytes, T* recs, cudaStream_t s) {
     const int64_t n = P.n_points;
     int end_bit = 1;
     while (end_bit < 32 && (1LL << end_bit) < P.u_comp_stride) ++end_bit;
@@ -255,11 +365,23 @@ cudaError_t plan_sort_points(const EvalParams<T>& P, uint32_t* perm, T* const* t
     uint32_t* vals_in = (uint32_t*)(base + 2 * arr);
     void* cub_tmp = base + 3 * arr;
     const unsigned nb = (unsigned)((n + BLOCK - 1) / BLOCK);
-    if (cells) plan_key_kernel<T, true><<<nb, BLOCK, 0, s>>>(P, keys_in, vals_in);
-    else plan_key_kernel<T, false><<<nb, BLOCK, 0, s>>>(P, keys_in, vals_in);
+    const int rec_elems = plan_rec_elems<T>(P.n_in);
+    if (cells) plan_key_kernel<T, true><<<nb, BLOCK, 0, s>>>(P, keys_in, vals_in, recs, rec_elems);
+    else plan_key_kernel<T, false><<<nb, BLOCK, 0, s>>>(P, keys_in, vals_in, recs, rec_elems);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     e = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, cells ? cells : keys_out, vals_in, perm, n, 0, end_bit, s);
     if (e != cudaSuccess) return e;
+    if (recs) {   // one random 32-byte read per point
+        GatherDst dst{};
+        for (int d = 0; d < P.n_in; ++d) dst.p[d] = t_sorted[d];
+        switch (P.n_in) {
+#define DIND_GR(NN) case NN: plan_gather_rec_kernel<T, NN><<<nb, BLOCK, 0, s>>>(recs, perm, dst, n); break;
+            DIND_GR(1) DIND_GR(2) DIND_GR(3) DIND_GR(4) DIND_GR(5) DIND_GR(6) DIND_GR(7) DIND_GR(8)
+#undef DIND_GR
+            default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
     for (int d = 0; d < P.n_in; ++d) {
         plan_gather_kernel<T><<<nb, BLOCK, 0, s>>>(P.dim[d].t_eval, perm, t_sorted[d], n);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -267,7 +389,7 @@ cudaError_t plan_sort_points(const EvalParams<T>& P, uint32_t* perm, T* const* t
     return cudaSuccess;
 }
 
-template cudaError_t plan_sort_points<float>(const EvalParams<float>&, uint32_t*, float* const*, uint32_t*, int, void*, size_t*, cudaStream_t);
-template cudaError_t plan_sort_points<double>(const EvalParams<double>&, uint32_t*, double* const*, uint32_t*, int, void*, size_t*, cudaStream_t);
+template cudaError_t plan_sort_points<float>(const EvalParams<float>&, uint32_t*, float* const*, uint32_t*, int, void*, size_t*, float*, cudaStream_t);
+template cudaError_t plan_sort_points<double>(const EvalParams<double>&, uint32_t*, double* const*, uint32_t*, int, void*, size_t*, double*, cudaStream_t);
 
 }  // namespace dind

@@ -535,10 +535,17 @@ def test_build_caches_is_optional_and_idempotent(D):
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("n", [1, 2047, 2048, 2049, 4097, 70001])
 @pytest.mark.parametrize("comps", [(), (2,), (3,), (4,), (5,)])
-def test_cell_sorted_window_boundaries_and_record_shapes(D, dtype, n, comps):
-    """The plan's two-level un-permutation works in windows of 2048 original points and in staging records of
-    8 / 16 / 32 / n*16 bytes: every window fill level and every record shape must give the unsorted result
-    bit for bit (value and fused gradient), and a re-plan after new t_eval must too."""
+@pytest.mark.parametrize("scheme", ["by-size", "buckets", "original-order", "buckets, per-dimension gathers"])
+def test_cell_sorted_window_boundaries_and_record_shapes(D, dtype, n, comps, scheme, monkeypatch):
+    """The plan brings results home through staging records of 8 / 16 / 32 / n*16 bytes, either in slots ordered by
+    windows of 2048 original points (records smaller than a sector) or at their original index (DIND_PLAN_BUCKETS
+    forces either): every window fill level and every record shape must give the unsorted result bit for bit (value
+    and fused gradient), and a re-plan after new t_eval must too.  DIND_NO_PLAN_RECS: sorted t_eval copies by one
+    gather per dimension instead of one record read per point."""
+    if scheme != "by-size":
+        monkeypatch.setenv("DIND_PLAN_BUCKETS", "0" if scheme == "original-order" else "1")
+    if scheme.endswith("gathers"):
+        monkeypatch.setenv("DIND_NO_PLAN_RECS", "1")
     rng = np.random.default_rng(n + 17 * len(comps) + (comps[0] if comps else 0))
     ts = [H.knots(rng, 7, dtype), H.knots(rng, 6, dtype)]
     u = rng.random((7, 6) + comps).astype(dtype)
