@@ -396,9 +396,7 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
             CUDA_TRY(plan_sort_points<T>(P, nullptr, ts, cells, cell_bits, nullptr, &scratch_bytes, nullptr, h->stream));
             // sort scratch (keys in/out, values in, CUB temp) stays with the handle: a new t_eval of the same
             // size re-plans without cudaMalloc / cudaFree (which would also synchronise the device)
-            size_t sb2 = 0;   // the un-permutation schedule sorts in the same scratch later
-            CUDA_TRY(plan_bucket_schedule(nullptr, nullptr, nullptr, n_points, nullptr, &sb2, h->stream));
-            CUDA_TRY(h->plan_scratch.ensure(std::max(scratch_bytes, sb2)));
+            CUDA_TRY(h->plan_scratch.ensure(scratch_bytes));
             // coordinate records for the one-read-per-point gather of the sorted t_eval: in the staging buffer of the
             // un-permutation (free at this point); without room for them the gathers run per dimension
             T* recs = nullptr;
@@ -449,9 +447,10 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
                     size_t sb2 = 0;
                     CUDA_TRY(plan_bucket_schedule(nullptr, nullptr, nullptr, n_points, nullptr, &sb2, h->stream));
                     CUDA_TRY(h->plan_scratch.ensure(sb2));
+                    sb2 = h->plan_scratch.cap;
                     CUDA_TRY(plan_bucket_schedule((const uint32_t*)h->plan_perm.p, (uint32_t*)h->plan_slot2.p,
                                                   (uint32_t*)h->plan_dest2.p, n_points, h->plan_scratch.p, &sb2, h->stream));
-                    h->launches += 3;
+                    h->launches += 1;
                     h->plan_buckets_valid = true;
                 }
                 P.perm = (const uint32_t*)h->plan_slot2.p;   // staging slot of plan position k

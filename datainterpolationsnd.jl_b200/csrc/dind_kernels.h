@@ -72,8 +72,9 @@ template <typename T> bool grid_split_slice_ok(const EvalParams<T>& P);   // the
 template <typename T> size_t grid_split_scratch_bytes(const EvalParams<T>& P);
 template <typename T> cudaError_t launch_grid_split(const EvalParams<T>& P, void* scratch, cudaStream_t s, const char** name, int* launches);
 
-// Two-level un-permutation (dind_plan.cu): slot2[k] = staging slot of plan position k (slots ordered by
-// the window of the destination), dest2[j] = destination of slot j; plan_unbucket copies slot j home.
+// Two-level un-permutation (dind_plan.cu): slot2[k] = staging slot of plan position k (slots grouped by the window of
+// the destination, handed out per window in arrival order from a cursor: one atomic per point, no sort),
+// dest2[j] = destination of slot j; plan_unbucket copies slot j home.  scratch: (n >> PLAN_WINDOW_SHIFT) + 1 counters.
 cudaError_t plan_bucket_schedule(const uint32_t* perm, uint32_t* slot2, uint32_t* dest2, int64_t n, void* scratch,
                                  size_t* scratch_bytes, cudaStream_t s);
 constexpr int PLAN_WINDOW_SHIFT = 11;   // windows of 2048 original points

@@ -90,27 +90,12 @@ __global__ void __launch_bounds__(BLOCK) plan_gather_kernel(const T* __restrict_
 // Bringing plan-ordered results back to the caller's order is a random permutation over the whole
 // output (config 3: 480 MB, config 5: 1.6 GB): as one gather it runs at DRAM-sector/TLB speed.
 // Instead the original index space is cut into windows of 2^shift points; the evaluation kernel
-// writes the result of plan position k to staging slot slot2[k], where the slots are ordered by
-// (window of the destination, k) — a few hundred sequential write streams that L2 write-combines —
-// and a second pass copies slot j to its destination dest2[j], which lies inside a window small
-// enough to be assembled in shared memory (plan_unbucket_kernel).
-__global__ void __launch_bounds__(BLOCK) bucket_key_kernel(const uint32_t* __restrict__ perm, uint32_t* __restrict__ keys,
-                                                           uint32_t* __restrict__ vals, int64_t n, int shift) {
-    const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-    if (k >= n) return;
-    keys[k] = __ldcs(perm + k) >> shift;
-    vals[k] = (uint32_t)k;
-}
-
-__global__ void __launch_bounds__(BLOCK) bucket_slots_kernel(const uint32_t* __restrict__ order2, const uint32_t* __restrict__ perm,
-                                                             uint32_t* __restrict__ slot2, uint32_t* __restrict__ dest2, int64_t n) {
-    const int64_t j = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-    if (j >= n) return;
-    const uint32_t k = __ldcs(order2 + j);
-    slot2[k] = (uint32_t)j;
-    dest2[j] = perm[k];
-}
-
+// writes the result of plan position k to staging slot slot2[k], where the slots of a window are handed
+// out in arrival order (bucket_cursor_kernel below) — every window's region fills front to back while the
+// kernel sweeps the plan, sequential write streams that L2 write-combines — and a second pass copies slot j
+// to its destination dest2[j], which lies inside a window small enough to be assembled in shared memory
+// (plan_unbucket_kernel).  Used for records smaller than a 32-byte sector; whole-sector records are staged
+// at their original index (plan_unstage below).
 // Second pass: one CTA per window of UNB_W original points.  The window's records are exactly the staging
 // slots [w * UNB_W, w * UNB_W + size) (the map is a permutation, so every window receives as many records
 // as it has points); they are read in order, dropped at their place in a shared-memory image of the
@@ -220,37 +205,6 @@ cudaError_t plan_build_items(const uint32_t* cells, int64_t n, int pts, uint32_t
     return cudaGetLastError();
 }
 
-cudaError_t plan_bucket_schedule(const uint32_t* perm, uint32_t* slot2, uint32_t* dest2, int64_t n, void* scratch,
-                                 size_t* scratch_bytes, cudaStream_t s) {
-    const int shift = PLAN_WINDOW_SHIFT;
-    int end_bit = 1;
-    while (end_bit < 32 && (1LL << end_bit) <= ((n - 1) >> shift)) ++end_bit;
-    size_t cub_bytes = 0;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, end_bit, s);
-    if (e != cudaSuccess) return e;
-    const size_t arr = ((size_t)n * sizeof(uint32_t) + 255) & ~(size_t)255;
-    const size_t need = 4 * arr + cub_bytes;   // keys in/out, values in/out (+ CUB temp)
-    if (!scratch) {
-        *scratch_bytes = need;
-        return cudaSuccess;
-    }
-    if (*scratch_bytes < need) return cudaErrorInvalidValue;
-    char* base = (char*)scratch;
-    uint32_t* keys_in = (uint32_t*)base;
-    uint32_t* keys_out = (uint32_t*)(base + arr);
-    uint32_t* vals_in = (uint32_t*)(base + 2 * arr);
-    uint32_t* order2 = (uint32_t*)(base + 3 * arr);
-    void* cub_tmp = base + 4 * arr;
-    const unsigned nb = (unsigned)((n + BLOCK - 1) / BLOCK);
-    bucket_key_kernel<<<nb, BLOCK, 0, s>>>(perm, keys_in, vals_in, n, shift);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    e = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_in, keys_out, vals_in, order2, n, 0, end_bit, s);   // stable
-    if (e != cudaSuccess) return e;
-    bucket_slots_kernel<<<nb, BLOCK, 0, s>>>(order2, perm, slot2, dest2, n);
-    return cudaGetLastError();
-}
-
 // ---- un-permutation through a staging buffer in ORIGINAL order ---------------------------------------------------
 // The evaluation kernel writes the result of plan position k as one aligned record to staged[perm[k]] (one random,
 // whole-sector store per point — the same write pattern as the window-ordered slots above, without the second sort
@@ -318,6 +272,36 @@ cudaError_t plan_unstage(const T* staged, T* out, int64_t n, int ct, int rec_str
 }
 template cudaError_t plan_unstage<float>(const float*, float*, int64_t, int, int, cudaStream_t);
 template cudaError_t plan_unstage<double>(const double*, double*, int64_t, int, int, cudaStream_t);
+
+// The slot schedule without a sort.  perm is a permutation, so window w receives exactly its own 2^shift points and
+// its slots are [w << shift, ...): plan position k takes the next free slot of its window from a cursor (one L2
+// atomic on n >> shift counters).  The kernel sweeps the plan front to back, so every window still fills (nearly) in
+// plan order — which is all the sequential-fill argument needs; which slot a record gets inside its window does not
+// change any result (plan_unbucket places it by dest2).
+__global__ void __launch_bounds__(BLOCK) bucket_cursor_kernel(const uint32_t* __restrict__ perm, uint32_t* __restrict__ cursor,
+                                                              uint32_t* __restrict__ slot2, uint32_t* __restrict__ dest2, int64_t n, int shift) {
+    const int64_t k = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t dest = __ldcs(perm + k);
+    const uint32_t w = dest >> shift;
+    const uint32_t j = (w << shift) + atomicAdd(cursor + w, 1u);
+    __stcs(slot2 + k, j);
+    dest2[j] = dest;
+}
+
+cudaError_t plan_bucket_schedule(const uint32_t* perm, uint32_t* slot2, uint32_t* dest2, int64_t n, void* scratch,
+                                        size_t* scratch_bytes, cudaStream_t s) {
+    const size_t need = (size_t)((n >> PLAN_WINDOW_SHIFT) + 1) * sizeof(uint32_t);
+    if (!scratch) {
+        *scratch_bytes = need;
+        return cudaSuccess;
+    }
+    if (*scratch_bytes < need) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, need, s);
+    if (e != cudaSuccess) return e;
+    bucket_cursor_kernel<<<(unsigned)((n + BLOCK - 1) / BLOCK), BLOCK, 0, s>>>(perm, (uint32_t*)scratch, slot2, dest2, n, PLAN_WINDOW_SHIFT);
+    return cudaGetLastError();
+}
 
 template <typename T>
 cudaError_t plan_unbucket(const T* staged, const uint32_t* dest2, T* out, int64_t n, int ct, int rec_stride, cudaStream_t s) {
