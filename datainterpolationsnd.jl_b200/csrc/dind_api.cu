@@ -67,6 +67,7 @@ Knobs read_knobs() {
     k.rec = geti("DIND_REC", -1);
     k.no_plan_recs = getenv("DIND_NO_PLAN_RECS") != nullptr;
     k.plan_buckets = geti("DIND_PLAN_BUCKETS", -1);
+    k.tile_smem = geti("DIND_TILE_SMEM", -1);
     return k;
 }
 

@@ -41,7 +41,28 @@ __device__ __forceinline__ void tile_weights(const DimParams<T>& D, T x, int idx
 
 // Axis-by-axis contraction for PT points that share the stencil: node loads are shared, the FMA chains are per point
 // (and per point identical to ContractV of dind_fast_unstructured_aos.cu).
-template <typename T, int D, int W, int C, int PT>
+// SMEM: the stencil was staged in shared memory (unstructured_tile_smem_kernel): plain loads instead of the read-only path
+template <typename T, int C>
+__device__ __forceinline__ Vec<T, C> load_node_smem(const T* p) {
+    Vec<T, C> r;
+    if constexpr (sizeof(T) == 8 && C >= 2) {
+        const double2 a = *reinterpret_cast<const double2*>(p);
+        r.v[0] = a.x;
+        r.v[1] = a.y;
+        if constexpr (C == 3) r.v[2] = p[2];
+        if constexpr (C == 4) {
+            const double2 b = *reinterpret_cast<const double2*>(p + 2);
+            r.v[2] = b.x;
+            r.v[3] = b.y;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) r.v[c] = p[c];
+    }
+    return r;
+}
+
+template <typename T, int D, int W, int C, int PT, bool SMEM = false>
 struct ContractT {
     static __device__ __forceinline__ void run(const T* __restrict__ p, const T (&w)[PT][MAXN][W], const int (&stride)[MAXN],
                                                T (&acc)[PT][C]) {
@@ -52,7 +73,7 @@ struct ContractT {
 #pragma unroll
         for (int a = 0; a < W; ++a) {
             T t[PT][C];
-            ContractT<T, D - 1, W, C, PT>::run(p + a * stride[D], w, stride, t);
+            ContractT<T, D - 1, W, C, PT, SMEM>::run(p + a * stride[D], w, stride, t);
 #pragma unroll
             for (int q = 0; q < PT; ++q)
 #pragma unroll
@@ -60,14 +81,17 @@ struct ContractT {
         }
     }
 };
-template <typename T, int W, int C, int PT>
-struct ContractT<T, 0, W, C, PT> {
+template <typename T, int W, int C, int PT, bool SMEM>
+struct ContractT<T, 0, W, C, PT, SMEM> {
     static __device__ __forceinline__ void run(const T* __restrict__ p, const T (&w)[PT][MAXN][W], const int (&)[MAXN],
                                                T (&acc)[PT][C]) {
         constexpr int S = C == 3 ? 4 : C;
         Vec<T, C> node[W];
 #pragma unroll
-        for (int a = 0; a < W; ++a) node[a] = load_node<T, C, false>(p + a * S);   // all loads of the row first
+        for (int a = 0; a < W; ++a) {   // all loads of the row first
+            if constexpr (SMEM) node[a] = load_node_smem<T, C>(p + a * S);
+            else node[a] = load_node<T, C, false>(p + a * S);
+        }
 #pragma unroll
         for (int q = 0; q < PT; ++q)
 #pragma unroll
@@ -178,6 +202,126 @@ __global__ void __launch_bounds__(TBLOCK, MINB) unstructured_tile_kernel(const _
         } else {
 #pragma unroll
             for (int c = 0; c < C; ++c) __stcs(P.out + (int64_t)c * P.out_comp_stride + (int64_t)ko[q] * P.out_point_stride, acc[q][c]);
+        }
+    }
+}
+
+// ---- the same kernel with the stencils staged in shared memory ---------------------------------------------------
+// ncu on the kernel above (config 3 in plan order, profiles/r2_c3_plan_order.md): FP64 pipe 56 % busy, 39 % of the L1
+// requests miss and the warps (3 per scheduler at 168 registers) wait for L2 on the nodes their FMA chains need —
+// long_scoreboard is the largest stall.  The items of a warp are consecutive in the plan, so they belong to two or
+// three consecutive cells (17 items per cell at 1e8 points).  Here every WARP finds its distinct cells (flag = the
+// cell differs from the previous lane's; ballot), copies each cell's 4 x 4 x 4 stencil (16 rows of 128 contiguous
+// bytes) from the component-fastest copy of u into a warp-private shared-memory slot with cp.async — issued before
+// the basis functions are computed, waited for after — and the contraction reads nodes from shared memory (lanes of
+// one cell read one address: broadcast; slots are 32 bytes apart modulo the bank cycle, so the cells of a warp do
+// not conflict).  No CTA barrier: warps stay decoupled and the FMA phase never waits on L2.  Same weights, same FMA
+// chains: bit-identical.  More distinct cells in a warp than slots (sparse plans): rounds of TS_SLOTS slots; the
+// launcher only picks this kernel where that is rare.  Nodes of 32 bytes only (Float64, 3 or 4 components).
+constexpr int TS_SLOTS = 6;   // per warp
+template <typename T, int C> struct TileSmem {
+    static constexpr int S = C == 3 ? 4 : C;
+    static constexpr int SLOT_ELEMS = 64 * S + 32 / (int)sizeof(T);   // 2048 + 32 bytes
+    static constexpr size_t BYTES = (size_t)(TBLOCK / 32) * TS_SLOTS * SLOT_ELEMS * sizeof(T);
+};
+
+template <typename T, int C, int PT, int MINB, int DER>
+__global__ void __launch_bounds__(TBLOCK, MINB) unstructured_tile_smem_kernel(const __grid_constant__ EvalParams<T> P, int pf_ctas) {
+    constexpr int N = 3, W = 4, S = TileSmem<T, C>::S, SLOT_ELEMS = TileSmem<T, C>::SLOT_ELEMS;
+    static_assert(S * sizeof(T) == 32, "32-byte nodes");
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    T* sm = reinterpret_cast<T*>(tile_smem) + wid * (TS_SLOTS * SLOT_ELEMS);
+    const int64_t i_raw = (int64_t)blockIdx.x * TBLOCK + tid;
+    const bool valid = i_raw < P.n_items;
+    const int64_t i = valid ? i_raw : P.n_items - 1;     // threads past the end repeat the last item (no new cell, no store)
+    const uint32_t cell = __ldcs(P.cells + i);
+    T xs[PT][N];
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+#pragma unroll
+        for (int q = 0; q < PT; ++q) xs[q][d] = __ldcs(P.dim[d].t_eval + i * PT + q);
+    const uint32_t s0 = __ldcs(P.items + i), s1 = __ldcs(P.items + i + 1);
+    {
+        const int64_t j = i_raw + (int64_t)pf_ctas * TBLOCK;
+        if (pf_ctas > 0 && j < P.n_items) {
+            tile_prefetch_l2(P.cells + j);
+            tile_prefetch_l2(P.items + j);
+#pragma unroll
+            for (int d = 0; d < N; ++d)
+#pragma unroll
+                for (int q = 0; q < PT; ++q) tile_prefetch_l2(P.dim[d].t_eval + j * PT + q);
+        }
+    }
+    int idx[N];
+    int64_t base = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        idx[d] = cell_idx<T>(P.dim[d], cell);
+        base += (int64_t)(idx[d] - W) * P.dim[d].u_stride;
+    }
+    // distinct cells of the warp -> slots
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, cell, 1);
+    const bool head = lane == 0 || cell != prev;
+    const unsigned bal = __ballot_sync(0xffffffffu, head);
+    const int slot = __popc(bal & (0xffffffffu >> (31 - lane))) - 1, total = __popc(bal);
+    const int64_t st1 = P.dim[1].u_stride, st2 = P.dim[2].u_stride;
+    // a stencil = 16 rows x 128 bytes = 128 chunks of 16 bytes: four per lane
+    int64_t ch_src[4];
+    unsigned ch_dst[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ch = lane + 32 * j, row = ch >> 3, part = (ch & 7) * (16 / (int)sizeof(T));
+        ch_src[j] = ((row & 3) * st1 + (row >> 2) * st2) * S + part;
+        ch_dst[j] = (unsigned)__cvta_generic_to_shared(sm + row * (4 * S) + part);
+    }
+    unsigned rem = bal;   // heads whose cells have not been staged yet
+    auto stage = [&](int first) {
+        const int last = min(total, first + TS_SLOTS);
+        for (int sl = first; sl < last; ++sl) {
+            const int64_t b = __shfl_sync(0xffffffffu, base, __ffs(rem) - 1);   // the sl-th distinct cell's first node
+            rem &= rem - 1;
+            const T* src = P.u_aos + b * S;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ch_dst[j] + (unsigned)((sl - first) * SLOT_ELEMS * sizeof(T))),
+                             "l"(src + ch_src[j])
+                             : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0);
+    T w[PT][MAXN][W];
+#pragma unroll
+    for (int d = 0; d < N; ++d)
+#pragma unroll
+        for (int q = 0; q < PT; ++q)
+            tile_weights<T, W>(P.dim[d], xs[q][d], idx[d], DER == -2 ? P.dim[d].order : (DER == d ? 1 : 0), w[q][d]);
+    const int cnt = valid ? (int)(s1 - s0) : 0;
+    uint32_t ko[PT];
+#pragma unroll
+    for (int q = 0; q < PT; ++q) ko[q] = (P.perm && q < cnt) ? __ldcs(P.perm + s0 + q) : s0 + q;
+    const int sstride[MAXN] = {S, 4 * S, 16 * S, 0, 0, 0, 0, 0};
+    for (int first = 0; first < total; first += TS_SLOTS) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (slot >= first && slot < first + TS_SLOTS) {
+            T acc[PT][C];
+            ContractT<T, N - 1, W, C, PT, true>::run(sm + (slot - first) * SLOT_ELEMS, w, sstride, acc);
+#pragma unroll
+            for (int q = 0; q < PT; ++q) {
+                if (q >= cnt) break;
+                if (P.staged_records) {
+                    store_record<T, C>(P.out + (int64_t)ko[q] * P.out_point_stride, acc[q]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) __stcs(P.out + (int64_t)c * P.out_comp_stride + (int64_t)ko[q] * P.out_point_stride, acc[q][c]);
+                }
+            }
+        }
+        if (first + TS_SLOTS < total) {   // sparse plan: another round of slots
+            __syncwarp();
+            stage(first + TS_SLOTS);
         }
     }
 }
@@ -460,6 +604,30 @@ cudaError_t launch_tile(const EvalParams<T>& P, cudaStream_t s) {
     for (int d = 0; d < N; ++d) {
         if (P.dim[d].order == 1 && der == -1) der = d;
         else if (P.dim[d].order != 0) der = -2;
+    }
+    if constexpr (N == 3 && W == 4 && sizeof(T) == 8 && (C == 3 || C == 4)) {
+        // stencils staged in shared memory where the plan is dense enough for a warp's items to share a few cells:
+        // >= 8 items per cell on average (<= 5 cells per warp, TS_SLOTS = 6)
+        double cells_total = 1.0;
+        for (int d = 0; d < N; ++d) cells_total *= (double)(P.dim[d].n_u - W + 1);
+        const int mode = P.knobs ? P.knobs->tile_smem : -1;
+        const bool dense = (double)P.n_items >= 8.0 * cells_total;
+        if (mode == 1 || (mode != 0 && dense)) {
+            const size_t smem = TileSmem<T, C>::BYTES;
+#define DIND_TILE_SM(DD)                                                                                                              \
+    do {                                                                                                                              \
+        cudaError_t e_ = cudaFuncSetAttribute(unstructured_tile_smem_kernel<T, C, PT, MINB, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e_ != cudaSuccess) return e_;                                                                                             \
+        unstructured_tile_smem_kernel<T, C, PT, MINB, DD><<<nb, TBLOCK, smem, s>>>(P, pf);                                            \
+    } while (0)
+            if (der == -1) DIND_TILE_SM(-1);
+            else if (der == 0) DIND_TILE_SM(0);
+            else if (der == 1) DIND_TILE_SM(1);
+            else if (der == 2) DIND_TILE_SM(2);
+            else DIND_TILE_SM(-2);
+#undef DIND_TILE_SM
+            return cudaGetLastError();
+        }
     }
 #define DIND_TILE(DD) unstructured_tile_kernel<T, N, W, C, PT, MINB, DD><<<nb, TBLOCK, 0, s>>>(P, pf)
     if (der == -1) DIND_TILE(-1);

@@ -695,6 +695,32 @@ def test_tile_kernel_variants_are_bit_identical(D, tile, shape, monkeypatch):
     ref_itp.close()
 
 
+@pytest.mark.parametrize("smem", ["0", "1"])
+@pytest.mark.parametrize("n_points,n_comp", [(60000, 3), (9000, 3), (1500, 3), (20000, 4), (128, 3), (1, 3)])
+def test_cubic_tile_kernel_shared_memory_staging(D, n_points, n_comp, smem, monkeypatch):
+    """DIND_TILE_SMEM=1: the cubic tile kernel stages every distinct cell of a CTA's items in shared memory (cp.async) and
+    contracts from there; more distinct cells than slots (sparse plans: 9000 / 1500 points over 1320 cells) go in rounds.
+    Bit-identical to the unsorted evaluation and to the global-memory variant, values and derivatives, both point orders."""
+    rng = np.random.default_rng(77 + n_points + n_comp)
+    kinds, degrees, n_knots = ("bspline",) * 3, (3, 3, 3), (12, 11, 13)
+    ts, u, _ = _case(rng, kinds, degrees, n_knots, (n_comp,), np.float64)
+    xs = [rng.uniform(t[0] - 0.05, t[-1] + 0.05, n_points) for t in ts]
+    mk = lambda: D.NDInterpolation(u, H.make_dims(D, kinds, ts, xs, degrees, None, max_deriv=[1] * 3))
+    ref_itp = mk()
+    monkeypatch.setenv("DIND_TILE_SMEM", smem)
+    itp = mk()
+    monkeypatch.delenv("DIND_TILE_SMEM")
+    for o in (None, (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0)):
+        ref = D.eval_unstructured(ref_itp, derivative_orders=o)
+        got = D.eval_unstructured(itp, derivative_orders=o, flags=CELL_SORTED)
+        assert np.array_equal(ref, got, equal_nan=True), (o, itp.last_kernel)
+        po = D.eval_unstructured(itp, derivative_orders=o, flags=CELL_SORTED | 32)
+        assert np.array_equal(ref[itp.plan_permutation()], po, equal_nan=True), (o, itp.last_kernel)
+    H.assert_close(D.eval_unstructured(itp, flags=CELL_SORTED), H.oracle_eval(kinds, ts, u, xs, degrees=degrees), np.float64)
+    itp.close()
+    ref_itp.close()
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("n_in,n_comp", [(2, 2), (3, 3), (3, 4), (4, 2), (4, 4), (5, 4), (5, 2), (6, 3)])
 def test_cell_record_table_is_bit_identical(D, n_in, n_comp, dtype, monkeypatch):
