@@ -17,6 +17,8 @@
 //
 // Reference: eval_unstructured! / eval_kernel (src/interpolation_parallel.jl:34-52, :105-138) evaluate one point
 // per work item and redo the whole stencil gather for each.
+#include <type_traits>
+
 #include "dind_kernels.h"
 
 namespace dind {
@@ -225,14 +227,60 @@ template <typename T, int C> struct TileSmem {
     static constexpr size_t BYTES = (size_t)(TBLOCK / 32) * TS_SLOTS * SLOT_ELEMS * sizeof(T);
 };
 
+// The warp's distinct cells and their shared-memory slots (see above).
+template <typename T, int C>
+struct WarpStencils {
+    static constexpr int S = TileSmem<T, C>::S, SLOT_ELEMS = TileSmem<T, C>::SLOT_ELEMS;
+    T* sm;            // the warp's TS_SLOTS slots
+    unsigned rem;     // heads whose cells have not been staged yet
+    int slot, total;  // this lane's slot; distinct cells of the warp
+    int64_t ch_src[4];
+    unsigned ch_dst[4];
+    __device__ __forceinline__ void init(unsigned char* smem, uint32_t cell, int64_t st1, int64_t st2) {
+        const int lane = threadIdx.x & 31;
+        sm = reinterpret_cast<T*>(smem) + (threadIdx.x >> 5) * (TS_SLOTS * SLOT_ELEMS);
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, cell, 1);
+        const bool head = lane == 0 || cell != prev;
+        rem = __ballot_sync(0xffffffffu, head);
+        slot = __popc(rem & (0xffffffffu >> (31 - lane))) - 1;
+        total = __popc(rem);
+        // a stencil = 16 rows x 128 bytes = 128 chunks of 16 bytes: four per lane
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ch = lane + 32 * j, row = ch >> 3, part = (ch & 7) * (16 / (int)sizeof(T));
+            ch_src[j] = ((row & 3) * st1 + (row >> 2) * st2) * S + part;
+            ch_dst[j] = (unsigned)__cvta_generic_to_shared(sm + row * (4 * S) + part);
+        }
+    }
+    // cp.async of the cells [first, first + TS_SLOTS) of the warp; base = this lane's first stencil node
+    __device__ __forceinline__ void stage(const T* __restrict__ u_aos, int64_t base, int first) {
+        const int last = min(total, first + TS_SLOTS);
+        for (int sl = first; sl < last; ++sl) {
+            const int64_t b = __shfl_sync(0xffffffffu, base, __ffs(rem) - 1);   // (__fns is a software loop: 32.4 vs 34.5 Gpoints/s)
+            rem &= rem - 1;
+            const T* src = u_aos + b * S;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ch_dst[j] + (unsigned)((sl - first) * SLOT_ELEMS * sizeof(T))),
+                             "l"(src + ch_src[j])
+                             : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ void wait() {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
+    __device__ __forceinline__ bool mine(int first) const { return slot >= first && slot < first + TS_SLOTS; }
+    __device__ __forceinline__ const T* stencil(int first) const { return sm + (slot - first) * SLOT_ELEMS; }
+};
+
 template <typename T, int C, int PT, int MINB, int DER>
 __global__ void __launch_bounds__(TBLOCK, MINB) unstructured_tile_smem_kernel(const __grid_constant__ EvalParams<T> P, int pf_ctas) {
-    constexpr int N = 3, W = 4, S = TileSmem<T, C>::S, SLOT_ELEMS = TileSmem<T, C>::SLOT_ELEMS;
+    constexpr int N = 3, W = 4, S = TileSmem<T, C>::S;
     static_assert(S * sizeof(T) == 32, "32-byte nodes");
     extern __shared__ __align__(16) unsigned char tile_smem[];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    T* sm = reinterpret_cast<T*>(tile_smem) + wid * (TS_SLOTS * SLOT_ELEMS);
-    const int64_t i_raw = (int64_t)blockIdx.x * TBLOCK + tid;
+    const int64_t i_raw = (int64_t)blockIdx.x * TBLOCK + threadIdx.x;
     const bool valid = i_raw < P.n_items;
     const int64_t i = valid ? i_raw : P.n_items - 1;     // threads past the end repeat the last item (no new cell, no store)
     const uint32_t cell = __ldcs(P.cells + i);
@@ -260,37 +308,9 @@ __global__ void __launch_bounds__(TBLOCK, MINB) unstructured_tile_smem_kernel(co
         idx[d] = cell_idx<T>(P.dim[d], cell);
         base += (int64_t)(idx[d] - W) * P.dim[d].u_stride;
     }
-    // distinct cells of the warp -> slots
-    const uint32_t prev = __shfl_up_sync(0xffffffffu, cell, 1);
-    const bool head = lane == 0 || cell != prev;
-    const unsigned bal = __ballot_sync(0xffffffffu, head);
-    const int slot = __popc(bal & (0xffffffffu >> (31 - lane))) - 1, total = __popc(bal);
-    const int64_t st1 = P.dim[1].u_stride, st2 = P.dim[2].u_stride;
-    // a stencil = 16 rows x 128 bytes = 128 chunks of 16 bytes: four per lane
-    int64_t ch_src[4];
-    unsigned ch_dst[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int ch = lane + 32 * j, row = ch >> 3, part = (ch & 7) * (16 / (int)sizeof(T));
-        ch_src[j] = ((row & 3) * st1 + (row >> 2) * st2) * S + part;
-        ch_dst[j] = (unsigned)__cvta_generic_to_shared(sm + row * (4 * S) + part);
-    }
-    unsigned rem = bal;   // heads whose cells have not been staged yet
-    auto stage = [&](int first) {
-        const int last = min(total, first + TS_SLOTS);
-        for (int sl = first; sl < last; ++sl) {
-            const int64_t b = __shfl_sync(0xffffffffu, base, __ffs(rem) - 1);   // the sl-th distinct cell's first node
-            rem &= rem - 1;
-            const T* src = P.u_aos + b * S;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ch_dst[j] + (unsigned)((sl - first) * SLOT_ELEMS * sizeof(T))),
-                             "l"(src + ch_src[j])
-                             : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    stage(0);
+    WarpStencils<T, C> ws;
+    ws.init(tile_smem, cell, P.dim[1].u_stride, P.dim[2].u_stride);
+    ws.stage(P.u_aos, base, 0);
     T w[PT][MAXN][W];
 #pragma unroll
     for (int d = 0; d < N; ++d)
@@ -302,12 +322,11 @@ __global__ void __launch_bounds__(TBLOCK, MINB) unstructured_tile_smem_kernel(co
 #pragma unroll
     for (int q = 0; q < PT; ++q) ko[q] = (P.perm && q < cnt) ? __ldcs(P.perm + s0 + q) : s0 + q;
     const int sstride[MAXN] = {S, 4 * S, 16 * S, 0, 0, 0, 0, 0};
-    for (int first = 0; first < total; first += TS_SLOTS) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-        if (slot >= first && slot < first + TS_SLOTS) {
+    for (int first = 0; first < ws.total; first += TS_SLOTS) {
+        ws.wait();
+        if (ws.mine(first)) {
             T acc[PT][C];
-            ContractT<T, N - 1, W, C, PT, true>::run(sm + (slot - first) * SLOT_ELEMS, w, sstride, acc);
+            ContractT<T, N - 1, W, C, PT, true>::run(ws.stencil(first), w, sstride, acc);
 #pragma unroll
             for (int q = 0; q < PT; ++q) {
                 if (q >= cnt) break;
@@ -319,9 +338,9 @@ __global__ void __launch_bounds__(TBLOCK, MINB) unstructured_tile_smem_kernel(co
                 }
             }
         }
-        if (first + TS_SLOTS < total) {   // sparse plan: another round of slots
+        if (first + TS_SLOTS < ws.total) {   // sparse plan: another round of slots
             __syncwarp();
-            stage(first + TS_SLOTS);
+            ws.stage(P.u_aos, base, first + TS_SLOTS);
         }
     }
 }
@@ -329,7 +348,7 @@ __global__ void __launch_bounds__(TBLOCK, MINB) unstructured_tile_smem_kernel(co
 // ---- fused value + first partials over work items (dind_eval_unstructured_gradient) -----------------------------
 // Same contraction as ContractGV of dind_fast_gradient.cu (per point the same FMAs in the same order: bit-identical
 // results), node loads shared by the item's PT points.
-template <typename T, int D, int W, int C, int PT>
+template <typename T, int D, int W, int C, int PT, bool SMEM = false>
 struct ContractGT {
     static __device__ __forceinline__ void run(const T* __restrict__ p, const T (&w)[PT][MAXN][W], const T (&dw)[PT][MAXN][W],
                                                const int (&stride)[MAXN], T (&r)[PT][(D + 2) * C]) {
@@ -340,7 +359,7 @@ struct ContractGT {
 #pragma unroll
         for (int a = 0; a < W; ++a) {
             T sub[PT][(D + 1) * C];
-            ContractGT<T, D - 1, W, C, PT>::run(p + a * stride[D], w, dw, stride, sub);
+            ContractGT<T, D - 1, W, C, PT, SMEM>::run(p + a * stride[D], w, dw, stride, sub);
 #pragma unroll
             for (int q = 0; q < PT; ++q) {
 #pragma unroll
@@ -351,14 +370,17 @@ struct ContractGT {
         }
     }
 };
-template <typename T, int W, int C, int PT>
-struct ContractGT<T, 0, W, C, PT> {
+template <typename T, int W, int C, int PT, bool SMEM>
+struct ContractGT<T, 0, W, C, PT, SMEM> {
     static __device__ __forceinline__ void run(const T* __restrict__ p, const T (&w)[PT][MAXN][W], const T (&dw)[PT][MAXN][W],
                                                const int (&)[MAXN], T (&r)[PT][2 * C]) {
         constexpr int S = C == 3 ? 4 : C;
         Vec<T, C> node[W];
 #pragma unroll
-        for (int a = 0; a < W; ++a) node[a] = load_node<T, C, false>(p + a * S);
+        for (int a = 0; a < W; ++a) {
+            if constexpr (SMEM) node[a] = load_node_smem<T, C>(p + a * S);
+            else node[a] = load_node<T, C, false>(p + a * S);
+        }
 #pragma unroll
         for (int q = 0; q < PT; ++q)
 #pragma unroll
@@ -375,10 +397,14 @@ struct ContractGT<T, 0, W, C, PT> {
     }
 };
 
-template <typename T, int N, int W, int C, int PT, int MINB>
+// SM: stencils staged in warp-private shared memory (WarpStencils above; N = 3, W = 4, 32-byte nodes)
+template <typename T, int N, int W, int C, int PT, int MINB, bool SM>
 __global__ void __launch_bounds__(TBLOCK, MINB) gradient_tile_kernel(const __grid_constant__ EvalParams<T> P, int pf_ctas) {
-    const int64_t i = (int64_t)blockIdx.x * TBLOCK + threadIdx.x;
-    if (i >= P.n_items) return;
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    const int64_t i_raw = (int64_t)blockIdx.x * TBLOCK + threadIdx.x;
+    const bool valid = i_raw < P.n_items;
+    if (!SM && !valid) return;
+    const int64_t i = valid ? i_raw : P.n_items - 1;     // SM: whole warps stay (threads past the end repeat the last item, store nothing)
     constexpr int S = C == 3 ? 4 : C;
     const uint32_t cell = __ldcs(P.cells + i);
     T xs[PT][N];
@@ -388,7 +414,7 @@ __global__ void __launch_bounds__(TBLOCK, MINB) gradient_tile_kernel(const __gri
         for (int q = 0; q < PT; ++q) xs[q][d] = __ldcs(P.dim[d].t_eval + i * PT + q);
     const uint32_t s0 = __ldcs(P.items + i), s1 = __ldcs(P.items + i + 1);
     {
-        const int64_t j = i + (int64_t)pf_ctas * TBLOCK;
+        const int64_t j = i_raw + (int64_t)pf_ctas * TBLOCK;
         if (pf_ctas > 0 && j < P.n_items) {
             tile_prefetch_l2(P.cells + j);
             tile_prefetch_l2(P.items + j);
@@ -408,6 +434,11 @@ __global__ void __launch_bounds__(TBLOCK, MINB) gradient_tile_kernel(const __gri
         stride[d] = (int)D.u_stride * S;
         base += (int64_t)(idx[d] - (W == 2 && D.kind == LINEAR ? 1 : W)) * D.u_stride;
     }
+    WarpStencils<T, C> ws;
+    if constexpr (SM) {
+        ws.init(tile_smem, cell, P.dim[1].u_stride, P.dim[2].u_stride);
+        ws.stage(P.u_aos, base, 0);
+    }
     T w[PT][MAXN][W], dw[PT][MAXN][W];
 #pragma unroll
     for (int d = 0; d < N; ++d)
@@ -416,33 +447,66 @@ __global__ void __launch_bounds__(TBLOCK, MINB) gradient_tile_kernel(const __gri
             tile_weights<T, W>(P.dim[d], xs[q][d], idx[d], 0, w[q][d]);
             tile_weights<T, W>(P.dim[d], xs[q][d], idx[d], 1, dw[q][d]);
         }
-    const int cnt = (int)(s1 - s0);
+    const int cnt = valid ? (int)(s1 - s0) : 0;
     uint32_t ko[PT];
 #pragma unroll
     for (int q = 0; q < PT; ++q) ko[q] = (P.perm && q < cnt) ? __ldcs(P.perm + s0 + q) : s0 + q;
-    T g[PT][(N + 1) * C];
-    ContractGT<T, N - 1, W, C, PT>::run(P.u_aos + base * S, w, dw, stride, g);
     const int64_t slot = P.out_comp_stride * C;
+    auto finish = [&](const T* stencil, const int (&st)[MAXN], auto smem_tag) {
+        T g[PT][(N + 1) * C];
+        ContractGT<T, N - 1, W, C, PT, decltype(smem_tag)::value>::run(stencil, w, dw, st, g);
 #pragma unroll
-    for (int q = 0; q < PT; ++q) {
-        if (q >= cnt) break;
-        T* o = P.out + (int64_t)ko[q] * P.out_point_stride;
-        if (P.staged_records) {
-            store_record<T, (N + 1) * C>(o, g[q]);
-        } else {
+        for (int q = 0; q < PT; ++q) {
+            if (q >= cnt) break;
+            T* o = P.out + (int64_t)ko[q] * P.out_point_stride;
+            if (P.staged_records) {
+                store_record<T, (N + 1) * C>(o, g[q]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < N + 1; ++j)
+                for (int j = 0; j < N + 1; ++j)
 #pragma unroll
-                for (int c = 0; c < C; ++c) __stcs(o + (int64_t)c * P.out_comp_stride + j * slot, g[q][j * C + c]);
+                    for (int c = 0; c < C; ++c) __stcs(o + (int64_t)c * P.out_comp_stride + j * slot, g[q][j * C + c]);
+            }
         }
+    };
+    if constexpr (SM) {
+        const int sstride[MAXN] = {S, 4 * S, 16 * S, 0, 0, 0, 0, 0};
+        for (int first = 0; first < ws.total; first += TS_SLOTS) {
+            ws.wait();
+            if (ws.mine(first)) finish(ws.stencil(first), sstride, std::true_type{});
+            if (first + TS_SLOTS < ws.total) {
+                __syncwarp();
+                ws.stage(P.u_aos, base, first + TS_SLOTS);
+            }
+        }
+    } else {
+        finish(P.u_aos + base * S, stride, std::false_type{});
     }
+}
+
+// plan dense enough for the shared-memory variants: >= 8 items per cell on average (<= 5 cells per warp, TS_SLOTS = 6)
+template <typename T, int N, int W>
+bool tile_smem_wanted(const EvalParams<T>& P) {
+    double cells_total = 1.0;
+    for (int d = 0; d < N; ++d) cells_total *= (double)(P.dim[d].n_u - W + 1);
+    const int mode = P.knobs ? P.knobs->tile_smem : -1;
+    return mode == 1 || (mode != 0 && (double)P.n_items >= 8.0 * cells_total);
 }
 
 template <typename T, int N, int W, int C, int PT, int MINB>
 cudaError_t launch_gradient_tile(const EvalParams<T>& P, cudaStream_t s) {
     const unsigned nb = (unsigned)((P.n_items + TBLOCK - 1) / TBLOCK);
     const int pf = (P.knobs && P.knobs->pf1 >= 0) ? P.knobs->pf1 : 2 * 148 * MINB;
-    gradient_tile_kernel<T, N, W, C, PT, MINB><<<nb, TBLOCK, 0, s>>>(P, pf);
+    if constexpr (N == 3 && W == 4 && sizeof(T) == 8 && (C == 3 || C == 4)) {
+        if (tile_smem_wanted<T, N, W>(P)) {
+            const size_t smem = TileSmem<T, C>::BYTES;
+            cudaError_t e = cudaFuncSetAttribute(gradient_tile_kernel<T, N, W, C, PT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            gradient_tile_kernel<T, N, W, C, PT, MINB, true><<<nb, TBLOCK, smem, s>>>(P, pf);
+            return cudaGetLastError();
+        }
+    }
+    gradient_tile_kernel<T, N, W, C, PT, MINB, false><<<nb, TBLOCK, 0, s>>>(P, pf);
     return cudaGetLastError();
 }
 
@@ -608,11 +672,7 @@ cudaError_t launch_tile(const EvalParams<T>& P, cudaStream_t s) {
     if constexpr (N == 3 && W == 4 && sizeof(T) == 8 && (C == 3 || C == 4)) {
         // stencils staged in shared memory where the plan is dense enough for a warp's items to share a few cells:
         // >= 8 items per cell on average (<= 5 cells per warp, TS_SLOTS = 6)
-        double cells_total = 1.0;
-        for (int d = 0; d < N; ++d) cells_total *= (double)(P.dim[d].n_u - W + 1);
-        const int mode = P.knobs ? P.knobs->tile_smem : -1;
-        const bool dense = (double)P.n_items >= 8.0 * cells_total;
-        if (mode == 1 || (mode != 0 && dense)) {
+        if (tile_smem_wanted<T, N, W>(P)) {
             const size_t smem = TileSmem<T, C>::BYTES;
 #define DIND_TILE_SM(DD)                                                                                                              \
     do {                                                                                                                              \

@@ -716,6 +716,9 @@ def test_cubic_tile_kernel_shared_memory_staging(D, n_points, n_comp, smem, monk
         assert np.array_equal(ref, got, equal_nan=True), (o, itp.last_kernel)
         po = D.eval_unstructured(itp, derivative_orders=o, flags=CELL_SORTED | 32)
         assert np.array_equal(ref[itp.plan_permutation()], po, equal_nan=True), (o, itp.last_kernel)
+    gref = D.eval_unstructured_gradient(ref_itp)
+    assert np.array_equal(gref, D.eval_unstructured_gradient(itp, flags=CELL_SORTED), equal_nan=True), itp.last_kernel
+    assert np.array_equal(gref[itp.plan_permutation()], D.eval_unstructured_gradient(itp, flags=CELL_SORTED | 32), equal_nan=True)
     H.assert_close(D.eval_unstructured(itp, flags=CELL_SORTED), H.oracle_eval(kinds, ts, u, xs, degrees=degrees), np.float64)
     itp.close()
     ref_itp.close()
