@@ -3,7 +3,8 @@ touches — u, weights, t_eval, out — sits in the middle of a larger allocatio
 are NaN, so a read outside an input poisons the result (caught by comparing with the evaluation of plain,
 unguarded arrays bit for bit); the guard bands around `out` hold a canary that must survive.  Covers every kernel
 family: pencil and two-stage grids, iid / plan-sorted / plan-order unstructured evaluation with the work-item tile
-kernels, the fused gradient, the generic fallback, and stencils that touch the first and last nodes of u."""
+kernels (shared-memory staging on and off), the cell-record gather, the fused gradient, the generic fallback, and
+stencils that touch the first and last nodes of u."""
 import numpy as np
 import pytest
 
@@ -73,8 +74,9 @@ UNSTRUCTURED = [
 ]
 
 
+@pytest.mark.parametrize("variant", ["default", "cell-record table, global-memory tile kernels"])
 @pytest.mark.parametrize("case", range(len(UNSTRUCTURED)))
-def test_unstructured_kernels_stay_inside_their_arrays(D, case):
+def test_unstructured_kernels_stay_inside_their_arrays(D, case, variant, monkeypatch):
     import torch
     kinds, degrees, n_knots, out_dims, dtype, n = UNSTRUCTURED[case]
     rng = np.random.default_rng(1000 + case)
@@ -84,7 +86,15 @@ def test_unstructured_kernels_stay_inside_their_arrays(D, case):
     xs = [points(rng, t, n, dtype) for t in ts]
     ref_itp = make(D, kinds, degrees, ts, [plain(torch, D, x) for x in xs], plain(torch, D, u))
     keep = [guarded(torch, x, float("nan")) for x in xs] + [guarded(torch, u, float("nan"))]
+    if variant != "default":
+        # the guarded handle gathers multilinear tables from the cell-record copy of u (dind_fast_unstructured_rec.cu)
+        # and runs the cubic tile kernels without their shared-memory staging; the reference handle keeps the defaults
+        # (small table: plain gather; dense plan: shared-memory staging) — same bits expected
+        monkeypatch.setenv("DIND_REC", "1")
+        monkeypatch.setenv("DIND_TILE_SMEM", "0")
     itp = make(D, kinds, degrees, ts, [k[1] for k in keep[:-1]], keep[-1][1])
+    monkeypatch.delenv("DIND_REC", raising=False)
+    monkeypatch.delenv("DIND_TILE_SMEM", raising=False)
     n_in = len(kinds)
     orders_list = [None, tuple(1 if d == n_in - 1 else 0 for d in range(n_in))]
     if "constant" in kinds:
