@@ -17,7 +17,7 @@ using Libdl
 export NDInterpolation, LinearInterpolationDimension, ConstantInterpolationDimension,
     BSplineInterpolationDimension, NURBSWeights, EmptyCache,
     eval_unstructured, eval_unstructured!, eval_grid, eval_grid!, eval_unstructured_gradient!, build_caches!,
-    set_u!, shard_range, comm_unique_id, init_comm!, allgather_out!
+    set_u!, shard_range, comm_unique_id, init_comm!, allgather_out!, eval_unstructured_allgather!
 
 # a const String: `ccall((:sym, libdind), ...)` needs a constant library expression
 const libdind = get(ENV, "LIBDIND", joinpath(@__DIR__, "..", "..", "..", "libdind.so"))
@@ -323,6 +323,22 @@ function allgather_out!(out_global::AbstractArray{T}, itp::NDInterpolation{N_in,
     GC.@preserve out_global out_local check(ccall((:dind_allgather_out, libdind), Cint,
         (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Cuint),
         itp.handle, dind_pointer(out_local), dind_pointer(out_global), n_total, unit, n_comp, 0))
+    return out_global
+end
+
+"""
+    eval_unstructured_allgather!(out_global, itp; n_total, derivative_orders, n_chunks = 0)
+
+Collective form of `eval_unstructured!` for a point-sharded evaluation: `itp` holds this rank's shard of the points
+(`shard_range`), the shard is evaluated straight into its rows of the device array `out_global` `(n_total, out...)` and
+the other ranks' rows arrive over NCCL while the next chunk of the shard is computed (dind_eval_unstructured_allgather).
+"""
+function eval_unstructured_allgather!(out_global::AbstractArray{T}, itp::NDInterpolation{N_in, N_out, T};
+        n_total::Integer, derivative_orders::NTuple{N_in, <:Integer} = ntuple(_ -> 0, N_in), n_chunks::Integer = 0) where {N_in, N_out, T}
+    @assert size(out_global) == (n_total, get_output_size(itp)...) "out_global must be (n_total, out...)"
+    o = orders_arg(derivative_orders)
+    GC.@preserve out_global o check(ccall((:dind_eval_unstructured_allgather, libdind), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cint}, Cint, Cuint), itp.handle, dind_pointer(out_global), n_total, o, n_chunks, 0))
     return out_global
 end
 
