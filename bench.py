@@ -510,6 +510,8 @@ def run_gpu(args, wl, rank, world, local_rank):
 
 # ---- the other BASELINE configs at their named sizes, in the same JSON line ---------------------------------------
 FMA_PEAK_TFMA = {"f64": 17.6, "f32": 32.3}   # register-resident FMA microbenchmark on B200 (scripts/microbench_fma.cu; profiles/r2_microbench.txt)
+L2_GATHER_GREQ_PER_S = 285.0                 # 32-byte requests per second (x 1e9) of a random gather from an L2-resident table, one lane per record
+                                             # (scripts/microbench_gather.cu; profiles/r2b_microbench_gather.txt: 17.8 Grecords/s x 16 loads)
 C3_FP64_OPS_PER_POINT = 378                  # 285 DFMA + 51 DADD + 42 DMUL per point and evaluation (ncu instruction mix)
 C3_GRADIENT_FP64_OPS_PER_POINT = 756         # fused value + 3 partials: contraction 384 + 144 + 48 FMA, order-0 and order-1 basis ~180
 
@@ -622,6 +624,16 @@ def bench_unstructured_family(D, torch, dist, wl, rank, world, local_rank, steps
                                         "peak": hbm, "unit": "GB/s", "frac": round(gbs / hbm, 4),
                                         "note": "cell-record copy of u (7.6 GB): one contiguous 512-byte block per point, requested as whole "
                                                 "128-byte lines by four lanes (dind_fast_unstructured_rec.cu)"}
+        if wl.key == "c3" and mode == "iid":
+            # iid order: every lane fetches its own 4 x 4 x 4 stencil from the L2-resident component-fastest copy (67 MB) as
+            # 64 requests of one 32-byte node; an SM completes about one such request per clock (the gather microbenchmark on
+            # an L2-resident table, one lane per record, 32-byte loads: profiles/r2b_microbench_gather.txt)
+            req = L2_GATHER_GREQ_PER_S
+            bound = req / 64.0
+            extra["roofline_gather"] = {"bound": "L1 miss requests of an L2-resident gather, iid point order", "requests_per_point": 64,
+                                        "peak_Grequests_per_s": req, "peak_Gpoints_per_s_per_gpu": round(bound, 2),
+                                        "frac": round(n / (ms * 1e-3) / 1e9 / bound, 4),
+                                        "note": "scripts/microbench_gather.cu, table of 64 MB, 32-byte loads, one lane per record"}
         res[mode] = _entry(wl, ms, n_total, alg, per_step, kernel, extra)
         if mode.startswith("gradient"):
             del gout

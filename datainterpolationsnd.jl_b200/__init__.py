@@ -311,7 +311,7 @@ class NDInterpolation:
         unchanged until `synchronize()`.
 
         A CUDA tensor is BORROWED (zero-copy), and the library keeps copies derived from it (the
-        component-fastest `u` of vector-valued fields, `u * weights` for NURBS): after changing a device
+        component-fastest `u` of vector-valued fields and its cell-record form for large multilinear tables, `u * weights` for NURBS): after changing a device
         `u` (or the weights) IN PLACE, call `set_u` again before evaluating."""
         a = _Arr(u, self.dtype)
         if len(a.shape) - self.N_in != self.N_out:

@@ -66,6 +66,7 @@ Knobs read_knobs() {
     k.persist = getenv("DIND_PERSIST") != nullptr;
     k.rec = geti("DIND_REC", -1);
     k.no_plan_recs = getenv("DIND_NO_PLAN_RECS") != nullptr;
+    k.no_batch_vec = getenv("DIND_NO_BATCH_VEC") != nullptr;
     k.plan_buckets = geti("DIND_PLAN_BUCKETS", -1);
     k.tile_smem = geti("DIND_TILE_SMEM", -1);
     return k;

@@ -63,26 +63,56 @@ __device__ __forceinline__ T ld_t(const T* p) {
     else return __ldg(p);
 }
 
-template <typename T, int W, int W4, bool NURBS, int REL, int PH, bool CO = false>
+// two adjacent batch columns as one 8- / 16-byte load or store
+template <typename T> struct Pair2;
+template <> struct Pair2<float> { using type = float2; };
+template <> struct Pair2<double> { using type = double2; };
+
+// VEC: the thread's two batch columns are ADJACENT (b, b + 1; B even): one vector load per row of T instead of two
+// scalar ones — half the loads, prefetches and address arithmetic of the walk (ncu: 22 of the 58 instructions per output
+// were integer address arithmetic, the kernel is bound by instruction issue).
+template <typename T, int W, int W4, bool NURBS, int REL, int PH, bool CO = false, bool VEC = false>
 __device__ __forceinline__ void batch_plane(const T* const (&bn)[SB_VB], int64_t pl, int64_t dd, int64_t stepB, int64_t rel_b,
                                             int64_t pf_off, bool pf_ok, const T (&w3)[2][W], T (&wn)[W4][2][SB_VB],
                                             T (&wd)[NURBS ? W4 : 1][2][SB_VB]) {
     constexpr int VB = SB_VB;
     constexpr int ROWS = REL == 2 ? 2 * W : W + REL;
     T rn[VB][ROWS], rd[VB][NURBS ? ROWS : 1];
-#pragma unroll
-    for (int v = 0; v < VB; ++v) {
-        const T* q = bn[v] + pl;
+    if constexpr (VEC) {
+        static_assert(SB_VB == 2 && !CO, "pair loads");
+        using P2 = typename Pair2<T>::type;
+        const T* q = bn[0] + pl;
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
-            rn[v][r] = ld_t<T, CO>(q);
-            if (NURBS) rd[v][r] = ld_t<T, CO>(q + dd);
-            // the walk is sequential along axis 4: ask for the same rows of the next plane now
+            const P2 a = __ldg(reinterpret_cast<const P2*>(q));
+            rn[0][r] = a.x;
+            rn[1][r] = a.y;
+            if (NURBS) {
+                const P2 d = __ldg(reinterpret_cast<const P2*>(q + dd));
+                rd[0][r] = d.x;
+                rd[1][r] = d.y;
+            }
             if (pf_ok) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(q + pf_off));
                 if (NURBS) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + dd + pf_off));
             }
             q += (REL == 2 && r == W - 1) ? rel_b : stepB;
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < VB; ++v) {
+            const T* q = bn[v] + pl;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                rn[v][r] = ld_t<T, CO>(q);
+                if (NURBS) rd[v][r] = ld_t<T, CO>(q + dd);
+                // the walk is sequential along axis 4: ask for the same rows of the next plane now
+                if (pf_ok) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(q + pf_off));
+                    if (NURBS) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + dd + pf_off));
+                }
+                q += (REL == 2 && r == W - 1) ? rel_b : stepB;
+            }
         }
     }
 #pragma unroll
@@ -103,7 +133,7 @@ __device__ __forceinline__ void batch_plane(const T* const (&bn)[SB_VB], int64_t
 
 // REL = 0 / 1: the two g_3 rows of the thread start at the same node / one node apart and share
 // their W + REL rows of T; REL = 2: unrelated rows (down-sampling, unsorted t_eval), loaded separately.
-template <typename T, int W, int W4, bool NURBS, int REL, bool CO = false>
+template <typename T, int W, int W4, bool NURBS, int REL, bool CO = false, bool VEC = false>
 __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s_i0, const T* s_w, int g_lo, int g_n,
                                            const int64_t (&boff)[SB_VB], const bool (&okb)[SB_VB], int g3a, bool ok1,
                                            int i3a, int i3b, const T (&w3)[2][W]) {
@@ -144,15 +174,15 @@ __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s
                 const int pidx = i4 + (W4 - shift) + s;
                 const bool pf_ok = pidx + SB_PF < Q.n4;
                 const int64_t pl = Bn3 * (int64_t)pidx;
-                if (W4 == 1 || phase == 0) batch_plane<T, W, W4, NURBS, REL, 0, CO>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
+                if (W4 == 1 || phase == 0) batch_plane<T, W, W4, NURBS, REL, 0, CO, VEC>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
                 if constexpr (W4 > 1) {
-                    if (phase == 1) batch_plane<T, W, W4, NURBS, REL, 1, CO>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
+                    if (phase == 1) batch_plane<T, W, W4, NURBS, REL, 1, CO, VEC>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
                 }
                 if constexpr (W4 > 2) {
-                    if (phase == 2) batch_plane<T, W, W4, NURBS, REL, 2, CO>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
+                    if (phase == 2) batch_plane<T, W, W4, NURBS, REL, 2, CO, VEC>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
                 }
                 if constexpr (W4 > 3) {
-                    if (phase == 3) batch_plane<T, W, W4, NURBS, REL, 3, CO>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
+                    if (phase == 3) batch_plane<T, W, W4, NURBS, REL, 3, CO, VEC>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
                 }
                 phase = phase + 1 == W4 ? 0 : phase + 1;
             }
@@ -192,13 +222,25 @@ __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s
 #pragma unroll
                 for (int v = 0; v < VB; ++v) qn[j][v] = nurbs_div_normal(qn[j][v], qd[j][v]);
         }
+        if constexpr (VEC) {
+            using P2 = typename Pair2<T>::type;
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int v = 0; v < VB; ++v) {
-                if (okb[v] && (j == 0 || ok1)) __stcs(op[j][v], qn[j][v]);
-                op[j][v] += o_plane;
+            for (int j = 0; j < 2; ++j) {
+                P2 pr;
+                pr.x = qn[j][0];
+                pr.y = qn[j][1];
+                if (okb[0] && (j == 0 || ok1)) __stcs(reinterpret_cast<P2*>(op[j][0]), pr);
+                op[j][0] += o_plane;
             }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int v = 0; v < VB; ++v) {
+                    if (okb[v] && (j == 0 || ok1)) __stcs(op[j][v], qn[j][v]);
+                    op[j][v] += o_plane;
+                }
+        }
     }
 }
 
@@ -211,7 +253,7 @@ __device__ __forceinline__ void group_sync() {
     else __syncthreads();
 }
 
-template <typename T, int W, int W4, bool NURBS, int NT, bool CO>
+template <typename T, int W, int W4, bool NURBS, int NT, bool CO, bool VEC = false>
 __device__ __forceinline__ void batch_body(const BatchParams<T>& Q, int bx, int by, int bseg0, int* s_i0, T* s_w, int tid) {
     const int g_lo = by * Q.chunk;
     const int g_n = min(Q.g4 - g_lo, Q.chunk);
@@ -227,9 +269,10 @@ __device__ __forceinline__ void batch_body(const BatchParams<T>& Q, int bx, int 
     bool okb[SB_VB];
 #pragma unroll
     for (int v = 0; v < SB_VB; ++v) {
-        const int64_t b = (int64_t)bseg * (32 * SB_VB) + lane + 32 * v;
+        // VEC: columns 2 * lane, 2 * lane + 1 of the segment (B is even: a pair is in or out as a whole)
+        const int64_t b = (int64_t)bseg * (32 * SB_VB) + (VEC ? SB_VB * lane + v : lane + 32 * v);
         okb[v] = b < Q.B;
-        boff[v] = okb[v] ? b : Q.B - 1;
+        boff[v] = okb[v] ? b : Q.B - (VEC ? SB_VB - v : 1);
     }
     const int g3a = g3p * 2;
     const bool ok1 = g3a + 1 < Q.g3;
@@ -242,16 +285,16 @@ __device__ __forceinline__ void batch_body(const BatchParams<T>& Q, int bx, int 
         w3[1][a] = __ldg(Q.w_3 + g3b * W + a);
     }
     const int rel = i3b - i3a;
-    if (rel == 0) batch_walk<T, W, W4, NURBS, 0, CO>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
-    else if (rel == 1) batch_walk<T, W, W4, NURBS, 1, CO>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
-    else batch_walk<T, W, W4, NURBS, 2, CO>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
+    if (rel == 0) batch_walk<T, W, W4, NURBS, 0, CO, VEC>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
+    else if (rel == 1) batch_walk<T, W, W4, NURBS, 1, CO, VEC>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
+    else batch_walk<T, W, W4, NURBS, 2, CO, VEC>(Q, s_i0, s_w, g_lo, g_n, boff, okb, g3a, ok1, i3a, i3b, w3);
 }
 
-template <typename T, int W, int W4, bool NURBS>
+template <typename T, int W, int W4, bool NURBS, bool VEC>
 __global__ void __launch_bounds__(SB_BLOCK, 4) grid_batch_kernel(const __grid_constant__ BatchParams<T> Q) {
     __shared__ int s_i0[SB_MAXCHUNK];
     __shared__ T s_w[SB_MAXCHUNK * W4];
-    batch_body<T, W, W4, NURBS, SB_BLOCK, false>(Q, blockIdx.x, blockIdx.y, 0, s_i0, s_w, threadIdx.x);
+    batch_body<T, W, W4, NURBS, SB_BLOCK, false, VEC>(Q, blockIdx.x, blockIdx.y, 0, s_i0, s_w, threadIdx.x);
 }
 
 // ---- stage 1 with the (n_1, n_2) slice of u in shared memory ----------------------------------------
@@ -520,7 +563,7 @@ cudaError_t launch_slice(const SliceParams<T>& Q, int64_t n_slices, cudaStream_t
 }
 
 template <typename T, int W, int W4>
-cudaError_t launch_batch(const BatchParams<T>& Q0, cudaStream_t s) {
+cudaError_t launch_batch(const BatchParams<T>& Q0, const Knobs* knobs, cudaStream_t s) {
     BatchParams<T> Q = Q0;
     Q.n_bseg = (int)((Q.B + 32 * SB_VB - 1) / (32 * SB_VB));
     const int64_t items = (int64_t)Q.n_bseg * ((Q.g3 + 1) / 2);
@@ -530,8 +573,17 @@ cudaError_t launch_batch(const BatchParams<T>& Q0, cudaStream_t s) {
     while (chunk > 8 && (int64_t)bx * ((Q.g4 + chunk - 1) / chunk) < 148 * 4 * 2) chunk >>= 1;
     Q.chunk = chunk;
     dim3 grid((unsigned)bx, (unsigned)((Q.g4 + chunk - 1) / chunk));
-    if (Q.td) grid_batch_kernel<T, W, W4, true><<<grid, SB_BLOCK, 0, s>>>(Q);
-    else grid_batch_kernel<T, W, W4, false><<<grid, SB_BLOCK, 0, s>>>(Q);
+    // adjacent column pairs (one vector load / store per pair) need an even B and pair-aligned arrays
+    const size_t pair = 2 * sizeof(T);
+    const bool vec = Q.B % 2 == 0 && (uintptr_t)Q.tn % pair == 0 && (uintptr_t)Q.td % pair == 0 && (uintptr_t)Q.out % pair == 0 &&
+                     !(knobs && knobs->no_batch_vec);
+    if (Q.td) {
+        if (vec) grid_batch_kernel<T, W, W4, true, true><<<grid, SB_BLOCK, 0, s>>>(Q);
+        else grid_batch_kernel<T, W, W4, true, false><<<grid, SB_BLOCK, 0, s>>>(Q);
+    } else {
+        if (vec) grid_batch_kernel<T, W, W4, false, true><<<grid, SB_BLOCK, 0, s>>>(Q);
+        else grid_batch_kernel<T, W, W4, false, false><<<grid, SB_BLOCK, 0, s>>>(Q);
+    }
     return cudaGetLastError();
 }
 
@@ -748,7 +800,7 @@ cudaError_t launch_grid_split(const EvalParams<T>& P, void* scratch, cudaStream_
         Q.n_bseg = Q.n_items = 0;
         const int W3 = P.dim[2].width, W4 = P.dim[3].width;
 #define DIND_BATCH(A, B4) \
-    if (W3 == A && W4 == B4) e = launch_batch<T, A, B4>(Q, s); else
+    if (W3 == A && W4 == B4) e = launch_batch<T, A, B4>(Q, P.knobs, s); else
         DIND_BATCH(3, 3) DIND_BATCH(4, 4) DIND_BATCH(1, 3) DIND_BATCH(3, 1) DIND_BATCH(1, 4) DIND_BATCH(4, 1) DIND_BATCH(1, 1)
         e = cudaErrorNotSupported;
 #undef DIND_BATCH

@@ -161,7 +161,8 @@ int dind_eval_unstructured_gradient(dind_handle_t handle, void* out, unsigned fl
  * set_basis_function_eval! (src/spline_utils.jl:164-191), i.e. everything that depends on
  * t_eval / u but not on the evaluation itself, so that the first evaluation does not pay for it:
  *   grid != 0: the per-axis index/weight tables eval_grid uses for `derivative_orders`;
- *   grid == 0: the component-fastest copy of u (vector-valued u), the per-point index cache with
+ *   grid == 0: the component-fastest copy of u (vector-valued u) and, for multilinear tables larger than L2 with enough
+ *              iid points to repay it, its cell-record copy; the per-point index cache with
  *              DIND_FLAG_CACHED_IDX, the cell-sorted plan with DIND_FLAG_CELL_SORTED.
  * Needs dind_set_dim, dind_set_t_eval and dind_set_u.  Evaluations build whatever is missing
  * lazily, so calling this is optional.  Honours DIND_FLAG_ASYNC. */

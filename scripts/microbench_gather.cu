@@ -67,7 +67,7 @@ int main() {
     float* out;
     CK(cudaMalloc(&out, n_pts * 4));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (double gb : {0.125, 0.5, 2.0, 8.0, 32.0}) {
+    for (double gb : {0.0625, 0.125, 0.5, 2.0, 8.0, 32.0}) {
         const size_t bytes = (size_t)(gb * (1ull << 30));
         char* tab;
         CK(cudaMalloc(&tab, bytes));

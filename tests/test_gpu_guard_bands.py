@@ -128,15 +128,17 @@ GRIDS = [
 ]
 
 
-@pytest.mark.parametrize("persist", [False, True])
+@pytest.mark.parametrize("persist", [False, True, "scalar batch loads"])
 @pytest.mark.parametrize("case", range(len(GRIDS)))
 def test_grid_kernels_stay_inside_their_arrays(D, case, persist, monkeypatch):
     import torch
     kinds, degrees, n_knots, out_dims, dtype, n_g, nurbs = GRIDS[case]
-    if persist and case != 1:
-        pytest.skip("the persistent two-stage kernel only takes 4-D all-B-spline grids")
-    if persist:
+    if persist and case not in ((1,) if persist is True else (1, 2)):
+        pytest.skip("variants of the two-stage 4-D kernels only")
+    if persist is True:
         monkeypatch.setenv("DIND_PERSIST", "1")
+    elif persist:
+        monkeypatch.setenv("DIND_NO_BATCH_VEC", "1")      # stage 2 with one scalar load per batch column (the odd-B path)
     rng = np.random.default_rng(2000 + case)
     ts = [knots(rng, k, dtype) for k in n_knots]
     n_u = [t.size + p - 1 if k == "bspline" else t.size for k, p, t in zip(kinds, degrees, ts)]
