@@ -421,11 +421,10 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
         P.coherent_points = 1;
         P.cells = (h->plan_has_cells && cell_bits > 0) ? (const uint32_t*)h->plan_cells.p : nullptr;
         P.perm = (flags & DIND_FLAG_PLAN_ORDER) ? nullptr : (const uint32_t*)h->plan_perm.p;
-        // Results go back to their original positions in two levels (dind_plan.cu): the kernel writes each
-        // result as one aligned record to a staging slot ordered by the 2048-point window of its destination,
-        // and a second pass assembles every window in shared memory and writes it out coalesced.  A direct
-        // scatter costs a random read-modify-write of a 32-byte sector per point AND component; a single
-        // gather pass over the whole staging buffer runs at DRAM-sector / TLB speed (measured: config 3
+        // Results go back to their original positions through a staging buffer of one aligned record per point
+        // (dind_plan.cu): the kernel writes the record, a second pass copies it home with coalesced reads and
+        // writes.  A direct scatter costs a random read-modify-write of a 32-byte sector per point AND component; a
+        // single gather pass over a plan-ordered staging buffer runs at DRAM-sector / TLB speed (measured: config 3
         // 0.81 ms vs 0.30 ms for 2e7 points, config 5 7 ms vs 1 ms for 1e8 points).
         // (Constant-with-derivative keeps the direct scatter: it must leave entries untouched.)
         if (P.perm && !const_deriv) {

@@ -45,6 +45,7 @@ struct BatchParams {
     const T* w_4;
     int chunk;
     int n_bseg, n_items;
+    int pf;               // planes of axis 4 the L2 prefetch runs ahead of the walk
 };
 
 __global__ void iota_kernel(int32_t* p, int n) {
@@ -155,6 +156,7 @@ __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s
     for (int v = 0; v < VB; ++v) bn[v] = Q.tn + boff[v] + Q.B * (int64_t)i3a;
     const int64_t dd = NURBS ? Q.td - Q.tn : 0;                       // same offsets in both stage-1 arrays
     const int64_t rel_b = Q.B * (int64_t)(i3b - i3a - (W - 1));       // REL == 2: jump from row i3a + W - 1 to row i3b
+    const int64_t pf_off = Q.pf * Bn3;   // L2 prefetch distance in planes
     int cur = -(1 << 30);
     int phase = 0;            // window slot that receives the next plane; plane cur + a lives in slot (phase + a) % W
     int rot[W4];               // rot[s] = (s - phase) mod W: the axis-4 weight that belongs to slot s
@@ -172,17 +174,17 @@ __device__ __forceinline__ void batch_walk(const BatchParams<T>& Q, const int* s
             const int shift = (i4 > cur && i4 - cur < W4) ? i4 - cur : W4;
             for (int s = 0; s < shift; ++s) {
                 const int pidx = i4 + (W4 - shift) + s;
-                const bool pf_ok = pidx + SB_PF < Q.n4;
+                const bool pf_ok = pidx + Q.pf < Q.n4;
                 const int64_t pl = Bn3 * (int64_t)pidx;
-                if (W4 == 1 || phase == 0) batch_plane<T, W, W4, NURBS, REL, 0, CO, VEC>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
+                if (W4 == 1 || phase == 0) batch_plane<T, W, W4, NURBS, REL, 0, CO, VEC>(bn, pl, dd, Q.B, rel_b, pf_off, pf_ok, w3, wn, wd);
                 if constexpr (W4 > 1) {
-                    if (phase == 1) batch_plane<T, W, W4, NURBS, REL, 1, CO, VEC>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
+                    if (phase == 1) batch_plane<T, W, W4, NURBS, REL, 1, CO, VEC>(bn, pl, dd, Q.B, rel_b, pf_off, pf_ok, w3, wn, wd);
                 }
                 if constexpr (W4 > 2) {
-                    if (phase == 2) batch_plane<T, W, W4, NURBS, REL, 2, CO, VEC>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
+                    if (phase == 2) batch_plane<T, W, W4, NURBS, REL, 2, CO, VEC>(bn, pl, dd, Q.B, rel_b, pf_off, pf_ok, w3, wn, wd);
                 }
                 if constexpr (W4 > 3) {
-                    if (phase == 3) batch_plane<T, W, W4, NURBS, REL, 3, CO, VEC>(bn, pl, dd, Q.B, rel_b, SB_PF * Bn3, pf_ok, w3, wn, wd);
+                    if (phase == 3) batch_plane<T, W, W4, NURBS, REL, 3, CO, VEC>(bn, pl, dd, Q.B, rel_b, pf_off, pf_ok, w3, wn, wd);
                 }
                 phase = phase + 1 == W4 ? 0 : phase + 1;
             }
@@ -572,6 +574,7 @@ cudaError_t launch_batch(const BatchParams<T>& Q0, const Knobs* knobs, cudaStrea
     int chunk = 32;
     while (chunk > 8 && (int64_t)bx * ((Q.g4 + chunk - 1) / chunk) < 148 * 4 * 2) chunk >>= 1;
     Q.chunk = chunk;
+    Q.pf = (knobs && knobs->pf1 > 0) ? knobs->pf1 : SB_PF;
     dim3 grid((unsigned)bx, (unsigned)((Q.g4 + chunk - 1) / chunk));
     // adjacent column pairs (one vector load / store per pair) need an even B and pair-aligned arrays
     const size_t pair = 2 * sizeof(T);
@@ -623,6 +626,7 @@ bool fused_plan(const EvalParams<T>& P, FusedParams<T>& F, size_t ctrl_ints_cap)
     F.s1_piece = piece;
     F.s1_sub = std::min(piece, 8);
     F.Q.chunk = chunk;
+    F.Q.pf = SB_PF;
     F.n_chunks4 = (int)((P.dim[3].n_eval + chunk - 1) / chunk);
     F.Q.n_bseg = (int)(b_tile / (32 * SB_VB));
     const int64_t items = (int64_t)F.Q.n_bseg * ((P.dim[2].n_eval + 1) / 2);

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(TBLOCK, MINB) unstructured_tile_kernel(const _
 #pragma unroll
     for (int q = 0; q < PT; ++q) {
         if (q >= cnt) break;
-        if (P.staged_records) {   // one aligned record per point (two-level un-permutation)
+        if (P.staged_records) {   // one aligned record per point (the plan's staging buffer)
             store_record<T, C>(P.out + (int64_t)ko[q] * P.out_point_stride, acc[q]);
         } else {
 #pragma unroll

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(BLOCK) plan_gather_kernel(const T* __restrict_
     if (k < n) dst[k] = src[perm[k]];
 }
 
-// ---- two-level un-permutation ------------------------------------------------------------------
+// ---- un-permutation through window-ordered staging slots (records smaller than a sector) ------------------------------------------------------------------
 // Bringing plan-ordered results back to the caller's order is a random permutation over the whole
 // output (config 3: 480 MB, config 5: 1.6 GB): as one gather it runs at DRAM-sector/TLB speed.
 // Instead the original index space is cut into windows of 2^shift points; the evaluation kernel
@@ -207,7 +207,7 @@ cudaError_t plan_build_items(const uint32_t* cells, int64_t n, int pts, uint32_t
 
 // ---- un-permutation through a staging buffer in ORIGINAL order ---------------------------------------------------
 // The evaluation kernel writes the result of plan position k as one aligned record to staged[perm[k]] (one random,
-// whole-sector store per point — the same write pattern as the window-ordered slots above, without the second sort
+// whole-sector store per point — the same write pattern as the window-ordered slots above, without the slot schedule
 // and its two index arrays); this pass reads the records in order and writes the component columns, both coalesced.
 constexpr int UNS_BLOCK = 256;
 template <typename T, int BYTES>
