@@ -67,6 +67,7 @@ Knobs read_knobs() {
     k.rec = geti("DIND_REC", -1);
     k.no_plan_recs = getenv("DIND_NO_PLAN_RECS") != nullptr;
     k.no_batch_vec = getenv("DIND_NO_BATCH_VEC") != nullptr;
+    k.no_den_cache = getenv("DIND_NO_DEN_CACHE") != nullptr;
     k.plan_buckets = geti("DIND_PLAN_BUCKETS", -1);
     k.tile_smem = geti("DIND_TILE_SMEM", -1);
     return k;
@@ -221,6 +222,7 @@ int ensure_table(dind_interp_s* h, int dim, int order) {
     CUDA_TRY(launch_axis_table<T>(P, order, (int32_t*)D.table.i0.p, (T*)D.table.w.p, (uint8_t*)D.table.flag.p, h->stream));
     h->launches += D.n_eval ? 1 : 0;
     D.table.order = order;
+    h->den_epoch++;   // a rebuilt axis table invalidates the cached stage-1 result of the NURBS weights
     return DIND_OK;
 }
 
@@ -340,10 +342,15 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     // NURBS numerator u*w: a separate pass per dind_set_u, except where the kernel forms it while staging u
     bool split = grid && !(flags & DIND_FLAG_GENERIC) && !const_deriv && !zero_result && grid_split_supported<T>(P) &&
                  !h->knobs.no_split;
-    if (split && h->split_scratch.ensure(grid_split_scratch_bytes<T>(P)) != cudaSuccess) {
-        cudaGetLastError();   // no room for the stage-1 results (at most 2x the size of out): one-pass kernel instead
-        split = false;
+    {
+        const void* before = h->split_scratch.p;
+        if (split && h->split_scratch.ensure(grid_split_scratch_bytes<T>(P)) != cudaSuccess) {
+            cudaGetLastError();   // no room for the stage-1 results (at most 2x the size of out): one-pass kernel instead
+            split = false;
+        }
+        if (h->split_scratch.p != before) h->den_epoch++;   // new scratch: nothing cached in it
     }
+    P.split_den_cached = split && h->w_set && h->split_den_epoch == h->den_epoch && !h->knobs.persist && !h->knobs.no_den_cache;
     P.u_is_raw = split && h->w_set && !h->uw_valid && grid_split_slice_ok<T>(P);
     if (!P.u_is_raw && (rc = ensure_premultiplied<T>(h))) return rc;
     P.u = (h->w_set && !P.u_is_raw) ? (const T*)h->uw.p : (const T*)h->d_u;
@@ -578,6 +585,8 @@ int run_eval(dind_interp_s* h, void* out, const int* orders, bool grid, const vo
     if (split && !handled) {
         err = launch_grid_split<T>(P, h->split_scratch.p, h->stream, &name, &nlaunch);
         handled = err != cudaErrorNotSupported;
+        if (err == cudaSuccess && h->w_set) h->split_den_epoch = h->den_epoch;
+        else h->split_den_epoch = 0;
         if (!handled) err = cudaSuccess;
     }
     if (fast_ok && !handled) {
@@ -847,6 +856,7 @@ int dind_set_dim(dind_handle_t h, int dim, int kind, const void* t, int64_t n_t,
     }
     DimState& D = h->dims[dim];
     D.set = false;   // from here on the device tables are being rewritten: a CUDA failure leaves the dimension unset
+    h->den_epoch++;
     D.invalidate_caches();
     h->plan_valid = false;
     D.kind = kind;
@@ -888,6 +898,7 @@ int dind_set_t_eval(dind_handle_t h, int dim, const void* t_eval, int64_t n_eval
     D.max_deriv = max_derivative_order_eval;
     D.teval_set = true;
     D.invalidate_caches();
+    h->den_epoch++;
     h->plan_valid = false;
     return DIND_OK;
 }
@@ -939,6 +950,7 @@ int dind_set_weights(dind_handle_t h, const void* weights, const int64_t* dims, 
     int rc = check_handle(h);
     if (rc) return rc;
     h->uw_valid = false;
+    h->den_epoch++;
     if (!weights) {
         h->w_set = false;
         h->d_w = nullptr;

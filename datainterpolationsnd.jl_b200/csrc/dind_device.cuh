@@ -147,7 +147,7 @@ struct Knobs {
     int pf1 = -1;        // DIND_PF1: L1 prefetch distance (-1 = default of the instantiation)
     int l2_warm = -1;    // DIND_L2_WARM: bulk L2 warm-up of u (-1 = default)
     int c3_tile = -1;    // DIND_C3_TILE: points per work item of the tile kernels (0 = one-point kernels, -1 = default)
-    bool no_lut = false, no_split = false, no_cells = false, no_aos = false, no_small = false, no_slice = false, no_plan_recs = false, no_batch_vec = false;
+    bool no_lut = false, no_split = false, no_cells = false, no_aos = false, no_small = false, no_slice = false, no_plan_recs = false, no_batch_vec = false, no_den_cache = false;
     int tile_smem = -1;      // DIND_TILE_SMEM: cubic tile kernel with the stencils staged in shared memory (1 / 0; -1 = where the plan is dense)
     int plan_buckets = -1;   // DIND_PLAN_BUCKETS: un-permutation through window-ordered slots (1) or original-order staging (0); -1 = by record size
     bool persist = false;      // DIND_PERSIST=1: the persistent two-stage 4-D grid kernel instead of two launches
@@ -179,6 +179,7 @@ struct EvalParams {
     int32_t n_stencil;       // grid: > 0 = dim[0..n_stencil) are the stencil axes and the rest identity/selector ("point") axes,
                              // already in kernel order (dind_fast_grid_split.cu); 0 = let the dispatcher classify the axes
     int32_t u_is_raw;        // NURBS: u has NOT been pre-multiplied by the weights (only the split grid path accepts that)
+    int32_t split_den_cached; // NURBS, split grid path: the denominator's stage-1 result is already in the scratch (same weights, knots, t_eval)
     int32_t coherent_points; // neighbouring points share their stencil (cell-sorted plan): prefer narrow, broadcast loads
     // cell-sorted plan, work items (dind_plan.cu: plan_build_items): item i = plan positions [items[i], items[i + 1]) —
     // at most item_pts consecutive points of ONE cell, evaluated by one thread that loads every stencil node once

@@ -759,8 +759,8 @@ cudaError_t launch_grid_split(const EvalParams<T>& P, void* scratch, cudaStream_
             return cudaSuccess;
         }
     }
-    bool den_done = false;
-    if (td && !use_slice) {
+    bool den_done = td && P.split_den_cached;   // the weights' stage-1 result of an earlier evaluation is still valid
+    if (td && !use_slice && !den_done) {
         P1.u = P.wts;
         P1.out = td;
         if (!try_eval_fast_grid<T>(P1, s, &nm, &e, &nl)) return cudaErrorNotSupported;

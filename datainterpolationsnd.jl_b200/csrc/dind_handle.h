@@ -107,6 +107,10 @@ struct dind_interp_s {
     dind::DevBuf uw;          // u pre-multiplied by the weights
     bool uw_valid = false;
     dind::DevBuf split_scratch;   // stage-1 results of the two-stage 4-D grid evaluation
+    // NURBS: the stage-1 result of the WEIGHTS (the denominator's T) depends on weights, knots and t_eval but not on u —
+    // "repeated with a new u" re-uses it.  den_epoch counts everything that invalidates it; split_den_epoch is the epoch
+    // at which the copy in split_scratch was computed (0 = none).
+    uint64_t den_epoch = 1, split_den_epoch = 0;
     dind::DevBuf u_aos;       // component-fastest copy of u (vector-valued unstructured evaluation)
     bool u_aos_valid = false;
     dind::DevBuf u_rec;       // cell-record copy of u_aos (multilinear tables larger than L2 at iid points)

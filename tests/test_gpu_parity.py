@@ -166,6 +166,50 @@ def test_nurbs_parity(D, dtype, flags, n_in, degree, out_dims):
     H.assert_close(got, ref, dtype)
 
 
+@pytest.mark.parametrize("out_dims", [(), (2,)])
+def test_nurbs_grid_denominator_cache_follows_weights_knots_and_t_eval(D, out_dims, monkeypatch):
+    """4-D NURBS grids (two-stage path): the stage-1 result of the WEIGHTS does not depend on u and is re-used when
+    eval_grid! is repeated with a new u (BASELINE config 4 in a loop).  It must be recomputed after new weights, new
+    t_eval, and never leak between them: every step equals a fresh handle with DIND_NO_DEN_CACHE bit for bit, and the
+    oracle within the tolerance."""
+    rng = np.random.default_rng(4242)
+    kinds, degrees = ("bspline",) * 4, (2,) * 4
+    ts, u, w = _case(rng, kinds, degrees, (7, 6, 7, 6), out_dims, np.float64, nurbs=True)
+    mkx = lambda n: [np.sort(H.query(rng, t, m, np.float64, outside=False)) for t, m in zip(ts, n)]
+    xg = mkx((12, 10, 11, 9))
+
+    def fresh(u_, w_, x_):
+        monkeypatch.setenv("DIND_NO_DEN_CACHE", "1")
+        itp = D.NDInterpolation(u_, H.make_dims(D, kinds, ts, x_, degrees), cache=D.NURBSWeights(w_))
+        monkeypatch.delenv("DIND_NO_DEN_CACHE")
+        out = D.eval_grid(itp)
+        assert itp.last_kernel.startswith("grid_split"), itp.last_kernel
+        itp.close()
+        return out
+
+    itp = D.NDInterpolation(u, H.make_dims(D, kinds, ts, xg, degrees), cache=D.NURBSWeights(w))
+    steps = []
+    u1 = rng.random(u.shape)
+    w1 = 0.5 + rng.random(w.shape)
+    xg1 = mkx((12, 10, 11, 9))
+    xg2 = mkx((10, 12, 9, 13))
+    steps.append(("first", lambda: None, u, w, xg))
+    steps.append(("new u", lambda: itp.set_u(u1), u1, w, xg))
+    steps.append(("same u again", lambda: None, u1, w, xg))
+    steps.append(("new weights", lambda: itp._set_weights(w1), u1, w1, xg))
+    steps.append(("new u after new weights", lambda: itp.set_u(u), u, w1, xg))
+    steps.append(("new t_eval, same sizes", lambda: itp.set_t_eval(xg1), u, w1, xg1))
+    steps.append(("new t_eval, other sizes", lambda: itp.set_t_eval(xg2), u, w1, xg2))
+    steps.append(("new u at the end", lambda: itp.set_u(u1), u1, w1, xg2))
+    for what, act, u_, w_, x_ in steps:
+        act()
+        got = D.eval_grid(itp)
+        assert itp.last_kernel.startswith("grid_split"), itp.last_kernel
+        assert np.array_equal(got, fresh(u_, w_, x_)), what
+        H.assert_close(got, H.oracle_eval(kinds, ts, u_, x_, degrees=degrees, weights=w_, grid=True), np.float64)
+    itp.close()
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("flags", [0, GENERIC])
 @pytest.mark.parametrize("grid", [False, True])
