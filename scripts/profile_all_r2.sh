@@ -14,7 +14,7 @@ one c1 unstructured_aos c1 ""
 one c3 unstructured_aos c3 "--full"
 one c3 unstructured_tile c3_sorted "--full --sorted"
 one c3 unstructured_tile c3_plan_order "--full --sorted --plan-order"
-one c3 gradient_tile c3_gradient "--full --sorted --plan-order --gradient fused"
+one c3 gradient_tile c3_gradient_plan_order "--full --sorted --plan-order --gradient fused"
 one c4 grid_batch c4 ""
 one c4 grid_slice c4_slice ""
 one c5 unstructured_aos c5 "--points 500000000"

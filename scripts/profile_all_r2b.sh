@@ -10,7 +10,7 @@ one() {   # workload, kernel regex, key, bench args
 }
 one c3 unstructured_tile_smem c3_plan_order "--full --sorted --plan-order"
 one c3 unstructured_tile_smem c3_sorted "--full --sorted"
-one c3 gradient_tile c3_gradient "--full --sorted --plan-order --gradient fused"
+one c3 gradient_tile c3_gradient_plan_order "--full --sorted --plan-order --gradient fused"
 one c4 grid_batch c4 ""
 one c5 linear_tile c5_sorted "--sorted"
 ls gpurun_out | grep r2b_ | head -30
