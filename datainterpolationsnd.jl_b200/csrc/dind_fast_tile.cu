@@ -484,7 +484,9 @@ __global__ void __launch_bounds__(TBLOCK, MINB) gradient_tile_kernel(const __gri
     }
 }
 
-// plan dense enough for the shared-memory variants: >= 8 items per cell on average (<= 5 cells per warp, TS_SLOTS = 6)
+// plan dense enough for the shared-memory variants: >= 8 items per cell on average (<= 5 cells per warp, TS_SLOTS = 6).
+// Measured (config 3 shape, plan order, shared memory vs global): 2e7 points (3.4 items per cell) 17.7 vs 24.8 Gpoints/s,
+// 5e7 (8.5) 29.4 vs 28.7, 1e8 (17) 34.5 vs 29.4.
 template <typename T, int N, int W>
 bool tile_smem_wanted(const EvalParams<T>& P) {
     double cells_total = 1.0;
