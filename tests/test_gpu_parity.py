@@ -166,6 +166,34 @@ def test_nurbs_parity(D, dtype, flags, n_in, degree, out_dims):
     H.assert_close(got, ref, dtype)
 
 
+def test_eval_unstructured_allgather_without_a_communicator(D):
+    """dind_eval_unstructured_allgather on ONE process (world = 1): the shard is the whole point list, the call is
+    eval_unstructured into the global array — in any number of chunks, bit for bit — and it validates its arguments
+    (the multi-GPU behaviour is tested by tests/c_abi_allgather.c and tests/multi_gpu_worker.py on >= 2 devices)."""
+    import torch
+    rng = np.random.default_rng(99)
+    kinds, degrees = ("linear",) * 3, (0,) * 3
+    ts, u, _ = _case(rng, kinds, degrees, (6, 5, 7), (3,), np.float64)
+    xs = H.zipped_queries(rng, ts, 30001, np.float64)
+    n = xs[0].size
+    itp = D.NDInterpolation(u, H.make_dims(D, kinds, ts, [torch.from_numpy(x).cuda() for x in xs], degrees))
+    ref = D.eval_unstructured(itp, derivative_orders=(0, 1, 0))
+    ref = ref.cpu().numpy() if hasattr(ref, "cpu") else np.asarray(ref)
+    for chunks in (0, 1, 7, 64, 1000):
+        full = D.f_empty((n, 3), np.float64, "cuda")
+        full.fill_(float("nan"))
+        D.eval_unstructured_allgather_(full, itp, n, derivative_orders=(0, 1, 0), n_chunks=chunks)
+        torch.cuda.synchronize()
+        assert np.array_equal(full.cpu().numpy(), ref), chunks
+    with pytest.raises(AssertionError):                       # the handle holds n points, not n + 1
+        D.eval_unstructured_allgather_(D.f_empty((n + 1, 3), np.float64, "cuda"), itp, n + 1)
+    with pytest.raises(AssertionError):                       # host array
+        D.eval_unstructured_allgather_(np.zeros((n, 3), order="F"), itp, n)
+    with pytest.raises(AssertionError):                       # wrong shape
+        D.eval_unstructured_allgather_(D.f_empty((n, 2), np.float64, "cuda"), itp, n)
+    itp.close()
+
+
 @pytest.mark.parametrize("out_dims", [(), (2,)])
 def test_nurbs_grid_denominator_cache_follows_weights_knots_and_t_eval(D, out_dims, monkeypatch):
     """4-D NURBS grids (two-stage path): the stage-1 result of the WEIGHTS does not depend on u and is re-used when
